@@ -1,0 +1,163 @@
+"""Pin the CPU oracle (oracle/logreg_oracle.py) to the reference.
+
+Two anchors: (1) the committed golden fixtures, which are outputs of the
+reference's own functions (tests/golden/make_golden.py); (2) when
+/root/reference is present (build container only), the live AST-lifted
+reference functions.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import logreg_oracle as O
+
+CHAINS_THREADED = {
+    # tag: (kind, kwargs)
+    "rwmh_t1": "rwmh", "rwmh_t50": "rwmh",
+    "mala_t1": "mala", "mala_t25": "mala", "mala_scalar_t1": "mala_scalar",
+}
+CHAINS_PLAIN = {
+    "ul_t1": "ul", "ul_t40": "ul",
+    "hmc_t1": "hmc", "hmc_t5": "hmc", "hmc_l7_t1": "hmc_l7",
+}
+
+
+def _target(g):
+    # the reference builds X column-major (pandas to_numpy + hstack);
+    # using the same layout keeps OpenBLAS on the same dgemv path => identical bits
+    return O.Target(np.asfortranarray(g["X"]), g["y"], g["pscale"])
+
+
+def test_known_answers_appendix_b(pima):
+    """SURVEY.md appendix B values, recomputed by the oracle."""
+    t = _target(pima)
+    z = np.zeros(8)
+    assert t.ll(z) == pytest.approx(-200 * np.log(2), rel=1e-14)
+    assert t.lprior(z) == pytest.approx(-9.654093358631428, rel=1e-14)
+    assert t.lpost(z) == pytest.approx(-148.28352947062046, rel=1e-14)
+    np.testing.assert_allclose(
+        t.glp(z), [-32.0, -28.0, -2533.0, -2054.0, -669.5, -870.8, -8.7675, -648.0], rtol=1e-12)
+    b0 = np.array([-9.8, 0.1, 0.03, -0.005, 0.0, 0.08, 1.8, 0.04])
+    assert t.lpost(b0) == pytest.approx(-103.86338162923353, rel=1e-13)
+
+
+def test_point_values_match_reference_outputs(pima):
+    t = _target(pima)
+    for i, b in enumerate(pima["B"]):
+        assert t.ll(b) == pytest.approx(pima["ll"][i], rel=1e-13)
+        assert t.lprior(b) == pytest.approx(pima["lprior"][i], rel=1e-13)
+        assert t.lprior(b) == pytest.approx(pima["lprior_fitnumpy"][i], rel=1e-13)
+        assert t.lpost(b) == pytest.approx(pima["lpost"][i], rel=1e-13)
+        np.testing.assert_allclose(t.glp(b), pima["glp"][i], rtol=1e-11, atol=1e-9)
+
+
+def test_synthetic_point_values(synth):
+    X = synth["X32"].astype(np.float64)
+    t = O.Target(X, synth["y"], synth["pscale"])
+    for i, b in enumerate(synth["B"]):
+        assert t.lpost(b) == pytest.approx(synth["lpost"][i], rel=1e-13)
+        np.testing.assert_allclose(t.glp(b), synth["glp"][i], rtol=1e-10, atol=1e-9)
+        lp, g = t.lpost_glp_chunked(b, chunk=300)
+        assert lp == pytest.approx(synth["lpost"][i], rel=1e-12)
+        np.testing.assert_allclose(g, synth["glp"][i], rtol=1e-9, atol=1e-9)
+        assert O.stable_ll(X, synth["y"], b) == pytest.approx(synth["ll"][i], rel=1e-12)
+
+
+def test_mala_closed_form_log_alpha(pima):
+    t = _target(pima)
+    b0 = pima["B"][1]
+    a = O.mala_log_alpha(t, b0, pima["mala_prop"], 1e-5, pima["pre"])
+    assert a == pytest.approx(float(pima["mala_log_alpha"]), rel=1e-9)
+    assert float(pima["mala_log_alpha"]) == pytest.approx(-29.492981396187382, rel=1e-9)
+
+
+def _run_oracle_chain(pima, tag, kind):
+    t = _target(pima)
+    seed, thin, iters = (int(v) for v in pima[tag + "_cfg"])
+    U = pima[tag + "_U"]
+    rng = O.ReplayRNG(pima[tag + "_Z"], U if U.size else None)
+    init = pima["chain_init"]
+    pre = pima["pre"]
+    if kind == "rwmh":
+        k = O.mh_kernel(t.lpost, O.rw_proposal(0.02 * pima["pre_rw"], rng), rng=rng)
+        return O.mcmc_threaded(init, k, thin, iters)
+    if kind == "mala":
+        return O.mcmc_threaded(init, O.mala_kernel(t.lpost, t.glp, 8, dt=1e-5, pre=pre, rng=rng), thin, iters)
+    if kind == "mala_scalar":
+        return O.mcmc_threaded(init, O.mala_kernel(t.lpost, t.glp, 8, dt=1e-6, rng=rng), thin, iters)
+    if kind == "ul":
+        return O.mcmc_plain(init, O.ul_kernel(t.glp, 8, dt=1e-6, pre=pre, rng=rng), thin, iters)
+    if kind == "hmc":
+        return O.mcmc_plain(init, O.hmc_kernel(t.lpost, t.glp, eps=1e-3, l=50, dmm=1 / pre, rng=rng), thin, iters)
+    if kind == "hmc_l7":
+        return O.mcmc_plain(init, O.hmc_kernel(t.lpost, t.glp, eps=2e-3, l=7, dmm=1 / pre, rng=rng), thin, iters)
+    raise AssertionError(kind)
+
+
+@pytest.mark.parametrize("tag,kind", list(CHAINS_THREADED.items()) + list(CHAINS_PLAIN.items()))
+def test_replayed_chains_bit_identical_to_reference(pima, tag, kind):
+    """The reference's chain under np.random.seed(s) == the oracle's chain fed
+    the pre-drawn (Z, U) stream: proves both the arithmetic and the RNG
+    consumption order."""
+    mat = _run_oracle_chain(pima, tag, kind)
+    ref = pima[tag + "_mat"]
+    assert mat.shape == ref.shape
+    # same arithmetic, same BLAS path => the difference is exactly 0 in the build
+    # container; 1e-9 leaves room for a different BLAS build on another host
+    np.testing.assert_allclose(mat, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_first_proposal_always_accepted(pima):
+    """ll starts at -inf (fit-numpy.py:66) so step 1 always moves."""
+    t = _target(pima)
+    # a move to a far worse point, with u ~ 1: still accepted on step 1, rejected on step 2
+    rng = O.ReplayRNG(np.ones((2, 8)), np.array([1.0 - 1e-16, 1.0 - 1e-16]))
+    k = O.mh_kernel(t.lpost, O.rw_proposal(np.ones(8), rng), rng=rng)
+    out = O.mcmc_threaded(np.zeros(8), k, 1, 2)
+    np.testing.assert_array_equal(out[0], np.ones(8))
+    np.testing.assert_array_equal(out[1], np.ones(8))
+    # and lp = -inf (naive overflow) on step 1 gives a = nan => rejected (hard part 8)
+    rng = O.ReplayRNG(np.ones((1, 8)) * 50.0, np.array([0.5]))
+    k = O.mh_kernel(t.lpost, O.rw_proposal(np.ones(8), rng), rng=rng)
+    with np.errstate(over="ignore", invalid="ignore"):
+        out = O.mcmc_threaded(np.zeros(8), k, 1, 1)
+    np.testing.assert_array_equal(out[0], np.zeros(8))
+
+
+def test_naive_ll_overflows_like_reference(pima):
+    t = _target(pima)
+    with np.errstate(over="ignore"):
+        assert t.ll(50 * np.ones(8)) == -np.inf
+    with np.errstate(over="ignore"):
+        assert np.all(np.isfinite(t.glp(50 * np.ones(8))))
+    assert np.isfinite(O.stable_ll(pima["X"], pima["y"], 50 * np.ones(8)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Python"), reason="reference tree not present")
+def test_against_live_reference(pima):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    X, y, n, p = mg.load_pima()
+    np.testing.assert_array_equal(X, pima["X"])
+    np.testing.assert_array_equal(y, pima["y"])
+    ns = mg.namespace("fit-np-hmc.py", {"ll", "pscale", "lprior", "lpost", "glp", "mhKernel", "hmcKernel", "mcmc"},
+                      X=X, y=y, n=n, p=p, init=np.zeros(p))
+    t = O.Target(X, y, ns["pscale"])
+    rs = np.random.RandomState(5)
+    for _ in range(20):
+        b = pima["map"] + rs.randn(8) * 0.05
+        assert t.lpost(b) == pytest.approx(ns["lpost"](b), rel=1e-14)
+        np.testing.assert_allclose(t.glp(b), ns["glp"](b), rtol=1e-12, atol=1e-10)
+    # a fresh chain, not in the fixtures
+    np.random.seed(99)
+    ref = ns["mcmc"](pima["map"], ns["hmcKernel"](ns["lpost"], ns["glp"], eps=1e-3, l=10, dmm=1 / pima["pre"]),
+                     thin=2, iters=15, verb=False)
+    np.random.seed(99)
+    Z, U = O.predraw(np.random, 30, 8)
+    rng = O.ReplayRNG(Z, U)
+    mine = O.mcmc_plain(pima["map"], O.hmc_kernel(t.lpost, t.glp, eps=1e-3, l=10, dmm=1 / pima["pre"], rng=rng), 2, 15)
+    np.testing.assert_allclose(mine, ref, rtol=1e-12, atol=1e-12)
