@@ -1,0 +1,903 @@
+// lrb_api.cu -- the C ABI of include/logreg_b200.h: handle, data binding,
+// evaluation, on-device sampler runs (CUDA-graph driven) and the row-sharded
+// communicators.  Host C++ only orchestrates; all arithmetic is in the kernels of
+// eval_kernel.cuh / sampler.cuh / data.cuh.  There is no CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/logreg_b200.h"
+#include "data.cuh"
+#include "eval_kernel.cuh"
+#include "sampler.cuh"
+
+using namespace lrb;
+
+namespace {
+
+thread_local std::string g_err;  // errors raised without a handle
+
+// ---- NCCL through dlopen: the library must load (and every single-GPU path must
+// work) on a box where libnccl is not on the loader path.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(const char* path, std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    err = "libnccl is missing required symbols";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+
+using EvalFn = void (*)(const EvalArgs);
+
+struct KernelChoice {
+  EvalFn grad = nullptr, nograd = nullptr;
+  int rows_per_batch = 0;
+};
+
+template <typename T, int P>
+KernelChoice choice() {
+  KernelChoice k;
+  k.grad = eval_kernel<T, P, true>;
+  k.nograd = eval_kernel<T, P, false>;
+  k.rows_per_batch = 512 * Chunk<T>::V / P;
+  return k;
+}
+
+template <typename T>
+bool pick_p(int P, KernelChoice& k) {
+  switch (P) {
+    case 8: k = choice<T, 8>(); return true;
+    case 16: k = choice<T, 16>(); return true;
+    case 32: k = choice<T, 32>(); return true;
+    case 64: k = choice<T, 64>(); return true;
+    case 128: k = choice<T, 128>(); return true;
+    case 256: k = choice<T, 256>(); return true;
+  }
+  return false;
+}
+
+int pad_p(int p) {
+  int P = 8;
+  while (P < p) P <<= 1;
+  return P;
+}
+
+}  // namespace
+
+struct lrb_handle {
+  int device = 0;
+  int sms = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+
+  // data
+  void* X = nullptr;
+  uint8_t* y = nullptr;
+  long long n = 0;
+  int p = 0, P = 0, mode = 0;
+  double* d_pscale = nullptr;     // [kMaxP]
+  double* d_logps = nullptr;      // [kMaxP]
+  bool bound = false;
+
+  // evaluation scratch
+  KernelChoice kern;
+  int grid = 0, grid_nograd = 0;
+  double* partials = nullptr;
+  unsigned int* ticket = nullptr;
+  double* sums = nullptr;   // [kMaxP+1]
+  double* res = nullptr;    // [kMaxP+3]
+  double* beta = nullptr;   // [kMaxP]
+  double* pinned = nullptr; // host staging [2*kMaxP+8]
+
+  // sampler
+  SamplerState* state = nullptr;
+  double* d_init = nullptr;   // [kMaxP]
+  double* d_scale = nullptr;  // [kMaxP]
+  double* d_out = nullptr; size_t out_cap = 0;
+  double* d_z = nullptr; size_t z_cap = 0;
+  double* d_u = nullptr; size_t u_cap = 0;
+  bool chain_live = false;    // a paused chain exists that a run may continue
+  int chain_kind = -1;
+  bool run_armed = false;
+  int run_kind = 0, run_l = 1;
+  bool run_want_grad = true;
+  bool pending_init_eval = false;
+  bool run_consumed = false;
+  const double* run_dz = nullptr;
+  const double* run_du = nullptr;
+  long long run_thin = 0, run_iters = 0;
+  lrb_sampler_params run_params{};
+  std::vector<double> run_scale;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_nodes = 0;
+  bool graph_grad = true;
+
+  // communicator
+  int world = 1, rank = 0, comm = 0;
+  ncclComm_t nccl = nullptr;
+  double* mailbox = nullptr;               // [2][kMaxRanks][kMailStride]
+  unsigned long long* flags = nullptr;     // [2][kMaxRanks], directly after the mailbox
+  unsigned long long* seq = nullptr;
+  void* peer_base[kMaxRanks] = {};
+  bool peer_open[kMaxRanks] = {};
+
+  long long kernel_launches = 0, eval_launches = 0;
+};
+
+namespace {
+
+constexpr size_t kMailDoubles = (size_t)2 * kMaxRanks * kMailStride;
+constexpr size_t kMailBytes = kMailDoubles * sizeof(double) + (size_t)2 * kMaxRanks * sizeof(unsigned long long);
+
+int fail(lrb_handle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_err = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(h, LRB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define CKN(h, call)                                                                      \
+  do {                                                                                    \
+    ncclResult_t r_ = (call);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      return fail(h, LRB_E_NCCL, "%s failed: %s", #call,                                  \
+                  g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");      \
+  } while (0)
+
+int use_device(lrb_handle* h) {
+  CK(h, cudaSetDevice(h->device));
+  return LRB_OK;
+}
+
+int free_data(lrb_handle* h) {
+  if (h->X) cudaFree(h->X);
+  if (h->y) cudaFree(h->y);
+  h->X = nullptr; h->y = nullptr; h->bound = false;
+  return LRB_OK;
+}
+
+void drop_graph(lrb_handle* h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  h->gexec = nullptr; h->graph = nullptr; h->graph_nodes = 0;
+}
+
+// choose kernels and grid for the bound shape
+int configure(lrb_handle* h) {
+  bool ok = h->mode == LRB_MODE_FP32 ? pick_p<float>(h->P, h->kern) : pick_p<double>(h->P, h->kern);
+  if (!ok) return fail(h, LRB_E_UNSUPPORTED, "unsupported padded column count %d", h->P);
+  int occ = 0, occ2 = 0;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kern.grad, kBlock, 0));
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, h->kern.nograd, kBlock, 0));
+  if (occ < 1 || occ2 < 1) return fail(h, LRB_E_CUDA, "fused kernel does not fit an SM");
+  const long long nbatch = (h->n + h->kern.rows_per_batch - 1) / h->kern.rows_per_batch;
+  const long long want = std::max<long long>(1, (nbatch + kWarps - 1) / kWarps);
+  h->grid = (int)std::min<long long>((long long)h->sms * occ, want);
+  h->grid_nograd = (int)std::min<long long>((long long)h->sms * occ2, want);
+  drop_graph(h);
+  h->chain_live = false;
+  h->run_armed = false;
+  return LRB_OK;
+}
+
+int set_prior(lrb_handle* h, const double* pscale) {
+  std::vector<double> ps(kMaxP, 1.0), lps(kMaxP, 0.0);
+  for (int j = 0; j < h->p; ++j) {
+    ps[j] = pscale ? pscale[j] : 1.0;
+    if (!(ps[j] > 0.0)) return fail(h, LRB_E_BAD_ARG, "pscale[%d] must be > 0", j);
+    lps[j] = std::log(ps[j]);
+  }
+  CK(h, cudaMemcpyAsync(h->d_pscale, ps.data(), kMaxP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_logps, lps.data(), kMaxP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return LRB_OK;
+}
+
+FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
+  FinishArgs f{};
+  f.beta = beta;
+  f.pscale = h->d_pscale;
+  f.log_pscale = h->d_logps;
+  f.res = h->res;
+  f.state = st;
+  f.p = h->p;
+  f.world = h->world;
+  f.rank = h->rank;
+  f.p2p = (h->comm == 2) ? 1 : 0;
+  f.mailbox_local = h->mailbox;
+  f.flags_local = h->flags;
+  f.seq = h->seq;
+  for (int r = 0; r < kMaxRanks; ++r) {
+    f.mailbox_peer[r] = nullptr;
+    f.flags_peer[r] = nullptr;
+    if (h->comm == 2 && r < h->world && h->peer_base[r]) {
+      f.mailbox_peer[r] = reinterpret_cast<double*>(h->peer_base[r]);
+      f.flags_peer[r] = reinterpret_cast<unsigned long long*>(
+          reinterpret_cast<char*>(h->peer_base[r]) + kMailDoubles * sizeof(double));
+    }
+  }
+  return f;
+}
+
+// Enqueue one fused evaluation at `beta` (device) on h->stream.
+int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_grad) {
+  EvalArgs a{};
+  a.X = h->X;
+  a.y = h->y;
+  a.n = h->n;
+  a.partials = h->partials;
+  a.ticket = h->ticket;
+  a.sums = h->sums;
+  a.fin = finish_args(h, beta, st);
+  const bool nccl_mode = (h->comm == 1 && h->world > 1);
+  a.fuse_finish = nccl_mode ? 0 : 1;
+  EvalFn fn = want_grad ? h->kern.grad : h->kern.nograd;
+  const int grid = want_grad ? h->grid : h->grid_nograd;
+  fn<<<grid, kBlock, 0, h->stream>>>(a);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  h->eval_launches++;
+  if (nccl_mode) {
+    CKN(h, g_nccl.AllReduce(h->sums, h->sums, (size_t)h->p + 1, ncclDouble, ncclSum, h->nccl, h->stream));
+    finish_kernel<<<1, kBlock, 0, h->stream>>>(a.fin, h->sums);
+    CK(h, cudaGetLastError());
+    h->kernel_launches++;
+  }
+  return LRB_OK;
+}
+
+template <typename ST, typename T>
+int ingest_launch(lrb_handle* h, const ST* src, bool colmajor, long long ld, long long nr, T* dst) {
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((nr + 31) / 32), (unsigned)((h->P + 31) / 32));
+  if (colmajor)
+    ingest_kernel<ST, T, true><<<grid, block, 0, h->stream>>>(src, ld, nr, h->p, dst, h->P);
+  else
+    ingest_kernel<ST, T, false><<<grid, block, 0, h->stream>>>(src, ld, nr, h->p, dst, h->P);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  return LRB_OK;
+}
+
+template <typename ST>
+int ingest_any(lrb_handle* h, const ST* src, bool colmajor, long long ld, long long nr, long long r0) {
+  if (h->mode == LRB_MODE_FP32)
+    return ingest_launch<ST, float>(h, src, colmajor, ld, nr, reinterpret_cast<float*>(h->X) + r0 * h->P);
+  return ingest_launch<ST, double>(h, src, colmajor, ld, nr, reinterpret_cast<double*>(h->X) + r0 * h->P);
+}
+
+int alloc_data(lrb_handle* h, long long n, int p, int mode) {
+  if (n <= 0 || p <= 0) return fail(h, LRB_E_BAD_ARG, "n and p must be positive (n=%lld p=%d)", n, p);
+  if (p > kMaxP) return fail(h, LRB_E_UNSUPPORTED, "p=%d exceeds the supported maximum %d", p, kMaxP);
+  if (mode != LRB_MODE_FP32 && mode != LRB_MODE_FP64) return fail(h, LRB_E_BAD_ARG, "bad mode %d", mode);
+  free_data(h);
+  h->n = n; h->p = p; h->P = pad_p(p); h->mode = mode;
+  const size_t es = mode == LRB_MODE_FP32 ? 4 : 8;
+  CK(h, cudaMalloc(&h->X, (size_t)n * h->P * es));
+  CK(h, cudaMalloc(&h->y, (size_t)n));
+  return LRB_OK;
+}
+
+}  // namespace
+
+// ============================================================ lifetime
+extern "C" int lrb_abi_version(void) { return LRB_ABI_VERSION; }
+
+extern "C" int lrb_device_count(int* count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess || c == 0) {
+    if (count) *count = 0;
+    return fail(nullptr, LRB_E_NO_DEVICE, "no CUDA device available (%s); logreg_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (count) *count = c;
+  return LRB_OK;
+}
+
+extern "C" int lrb_create(int device, lrb_handle** out) {
+  if (!out) return fail(nullptr, LRB_E_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  int c = 0;
+  int rc = lrb_device_count(&c);
+  if (rc != LRB_OK) return rc;
+  if (device < 0 || device >= c) return fail(nullptr, LRB_E_BAD_ARG, "device %d out of range (%d devices)", device, c);
+  lrb_handle* h = new lrb_handle();
+  h->device = device;
+  auto bail = [&](int code) { g_err = h->err; lrb_destroy(h); return code; };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(h, LRB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LRB_E_CUDA); } } while (0)
+  CKC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    fail(h, LRB_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return bail(LRB_E_UNSUPPORTED);
+  }
+  h->sms = prop.multiProcessorCount;
+  CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CKC(cudaMalloc(&h->d_pscale, kMaxP * sizeof(double)));
+  CKC(cudaMalloc(&h->d_logps, kMaxP * sizeof(double)));
+  CKC(cudaMalloc(&h->partials, (size_t)h->sms * 8 * (kMaxP + 1) * sizeof(double)));
+  CKC(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+  CKC(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  CKC(cudaMalloc(&h->sums, (kMaxP + 1) * sizeof(double)));
+  CKC(cudaMalloc(&h->res, (kMaxP + 3) * sizeof(double)));
+  CKC(cudaMalloc(&h->beta, kMaxP * sizeof(double)));
+  CKC(cudaMalloc(&h->d_init, kMaxP * sizeof(double)));
+  CKC(cudaMalloc(&h->d_scale, kMaxP * sizeof(double)));
+  CKC(cudaMalloc(&h->state, sizeof(SamplerState)));
+  CKC(cudaMemset(h->state, 0, sizeof(SamplerState)));
+  CKC(cudaMalloc(&h->seq, sizeof(unsigned long long)));
+  CKC(cudaMemset(h->seq, 0, sizeof(unsigned long long)));
+  CKC(cudaMallocHost(&h->pinned, (2 * kMaxP + 8) * sizeof(double)));
+#undef CKC
+  *out = h;
+  return LRB_OK;
+}
+
+extern "C" int lrb_destroy(lrb_handle* h) {
+  if (!h) return LRB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
+  if (h->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+  free_data(h);
+  void* bufs[] = {h->d_pscale, h->d_logps, h->partials, h->ticket, h->sums, h->res, h->beta, h->d_init,
+                  h->d_scale, h->state, h->seq, h->d_out, h->d_z, h->d_u, h->mailbox};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return LRB_OK;
+}
+
+extern "C" const char* lrb_last_error(const lrb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+extern "C" int lrb_set_stream(lrb_handle* h, void* cuda_stream) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  drop_graph(h);  // graphs are captured per stream
+  return LRB_OK;
+}
+
+extern "C" int lrb_synchronize(lrb_handle* h) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return LRB_OK;
+}
+
+extern "C" int lrb_get_info(const lrb_handle* h, lrb_info* info) {
+  if (!h || !info) return fail(nullptr, LRB_E_BAD_ARG, "NULL argument");
+  info->n = h->n; info->p = h->p; info->p_pad = h->P; info->mode = h->mode;
+  info->grid = h->grid; info->block = kBlock; info->world = h->world; info->rank = h->rank;
+  info->comm = h->comm;
+  info->bytes_per_eval = h->n * h->p * (h->mode == LRB_MODE_FP32 ? 4 : 8) + h->n;
+  info->kernel_launches = h->kernel_launches;
+  info->eval_launches = h->eval_launches;
+  return LRB_OK;
+}
+
+// ============================================================ data
+extern "C" int lrb_bind_data(lrb_handle* h, const void* X, int x_dtype, int layout, int64_t ld,
+                             const void* y, int y_dtype, int64_t n, int p, const double* pscale,
+                             int mode, int location) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!X || !y) return fail(h, LRB_E_BAD_ARG, "X and y must not be NULL");
+  if (x_dtype != LRB_F32 && x_dtype != LRB_F64) return fail(h, LRB_E_BAD_ARG, "X dtype must be F32 or F64");
+  if (layout != LRB_ROW_MAJOR && layout != LRB_COL_MAJOR) return fail(h, LRB_E_BAD_ARG, "bad layout %d", layout);
+  if (location != LRB_HOST && location != LRB_DEVICE) return fail(h, LRB_E_BAD_ARG, "bad location %d", location);
+  const bool colmajor = layout == LRB_COL_MAJOR;
+  if (ld < (colmajor ? n : (int64_t)p)) return fail(h, LRB_E_BAD_ARG, "leading dimension %lld too small", (long long)ld);
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  int rc = alloc_data(h, n, p, mode);
+  if (rc) return rc;
+  rc = set_prior(h, pscale);
+  if (rc) return rc;
+  const size_t es = x_dtype == LRB_F32 ? 4 : 8;
+
+  if (location == LRB_DEVICE) {
+    rc = x_dtype == LRB_F32 ? ingest_any<float>(h, (const float*)X, colmajor, ld, n, 0)
+                            : ingest_any<double>(h, (const double*)X, colmajor, ld, n, 0);
+    if (rc) return rc;
+  } else {
+    // stage row blocks (<= 256 MB) through device memory, re-laying each out
+    long long chunk = std::max<long long>(1, (256ll << 20) / ((long long)p * (long long)es));
+    chunk = std::min<long long>(chunk, n);
+    void* stage = nullptr;
+    CK(h, cudaMalloc(&stage, (size_t)chunk * p * es));
+    for (long long r0 = 0; r0 < n; r0 += chunk) {
+      const long long nr = std::min<long long>(chunk, n - r0);
+      cudaError_t e;
+      if (colmajor)
+        e = cudaMemcpy2DAsync(stage, (size_t)nr * es, (const char*)X + (size_t)r0 * es, (size_t)ld * es,
+                              (size_t)nr * es, (size_t)p, cudaMemcpyHostToDevice, h->stream);
+      else
+        e = cudaMemcpy2DAsync(stage, (size_t)p * es, (const char*)X + (size_t)r0 * ld * es, (size_t)ld * es,
+                              (size_t)p * es, (size_t)nr, cudaMemcpyHostToDevice, h->stream);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(h, LRB_E_CUDA, "X upload failed: %s", cudaGetErrorString(e)); }
+      const long long sld = colmajor ? nr : p;
+      rc = x_dtype == LRB_F32 ? ingest_any<float>(h, (const float*)stage, colmajor, sld, nr, r0)
+                              : ingest_any<double>(h, (const double*)stage, colmajor, sld, nr, r0);
+      if (rc) { cudaFree(stage); return rc; }
+      e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(h, LRB_E_CUDA, "X ingest failed: %s", cudaGetErrorString(e)); }
+    }
+    cudaFree(stage);
+  }
+
+  // y -> u8 with validation
+  int* d_bad = nullptr;
+  CK(h, cudaMalloc(&d_bad, sizeof(int)));
+  CK(h, cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+  const size_t ys = y_dtype == LRB_F32 ? 4 : y_dtype == LRB_F64 ? 8 : 1;
+  if (y_dtype != LRB_F32 && y_dtype != LRB_F64 && y_dtype != LRB_U8) { cudaFree(d_bad); return fail(h, LRB_E_BAD_ARG, "bad y dtype"); }
+  const void* ysrc = y;
+  void* ystage = nullptr;
+  if (location == LRB_HOST) {
+    CK(h, cudaMalloc(&ystage, (size_t)n * ys));
+    CK(h, cudaMemcpyAsync(ystage, y, (size_t)n * ys, cudaMemcpyHostToDevice, h->stream));
+    ysrc = ystage;
+  }
+  const unsigned gy = (unsigned)((n + 255) / 256);
+  if (y_dtype == LRB_F32) ingest_y_kernel<float><<<gy, 256, 0, h->stream>>>((const float*)ysrc, n, h->y, d_bad);
+  else if (y_dtype == LRB_F64) ingest_y_kernel<double><<<gy, 256, 0, h->stream>>>((const double*)ysrc, n, h->y, d_bad);
+  else ingest_y_kernel<uint8_t><<<gy, 256, 0, h->stream>>>((const uint8_t*)ysrc, n, h->y, d_bad);
+  h->kernel_launches++;
+  int bad = 0;
+  cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (ystage) cudaFree(ystage);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "y ingest failed: %s", cudaGetErrorString(e));
+  if (bad) { free_data(h); return fail(h, LRB_E_BAD_ARG, "y must contain only 0 and 1"); }
+  rc = configure(h);
+  if (rc) return rc;
+  h->bound = true;
+  return LRB_OK;
+}
+
+extern "C" int lrb_gen_synthetic(lrb_handle* h, int64_t n_local, int p, int mode, uint64_t seed,
+                                 const double* beta_true, const double* pscale, int64_t row_offset) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!beta_true) return fail(h, LRB_E_BAD_ARG, "beta_true is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  int rc = alloc_data(h, n_local, p, mode);
+  if (rc) return rc;
+  rc = set_prior(h, pscale);
+  if (rc) return rc;
+  double* d_bt = nullptr;
+  CK(h, cudaMalloc(&d_bt, kMaxP * sizeof(double)));
+  CK(h, cudaMemcpyAsync(d_bt, beta_true, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const long long nthreads = n_local * (h->P / 4);
+  const unsigned gx = (unsigned)((nthreads + 255) / 256), gy = (unsigned)((n_local + 255) / 256);
+  if (mode == LRB_MODE_FP32) {
+    synth_x_kernel<float><<<gx, 256, 0, h->stream>>>((float*)h->X, n_local, p, h->P, seed, row_offset);
+    synth_y_kernel<float><<<gy, 256, 0, h->stream>>>((const float*)h->X, n_local, p, h->P, d_bt, seed, row_offset, h->y);
+  } else {
+    synth_x_kernel<double><<<gx, 256, 0, h->stream>>>((double*)h->X, n_local, p, h->P, seed, row_offset);
+    synth_y_kernel<double><<<gy, 256, 0, h->stream>>>((const double*)h->X, n_local, p, h->P, d_bt, seed, row_offset, h->y);
+  }
+  h->kernel_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_bt);
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "synthetic generation failed: %s", cudaGetErrorString(e));
+  rc = configure(h);
+  if (rc) return rc;
+  h->bound = true;
+  return LRB_OK;
+}
+
+extern "C" int lrb_copy_rows(lrb_handle* h, int64_t row0, int64_t nrows, double* X_out, float* y_out) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "no data bound");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > h->n) return fail(h, LRB_E_BAD_ARG, "row range out of bounds");
+  if (nrows == 0) return LRB_OK;
+  if (use_device(h)) return LRB_E_CUDA;
+  double* dX = nullptr; float* dy = nullptr;
+  CK(h, cudaMalloc(&dX, (size_t)nrows * h->p * sizeof(double)));
+  CK(h, cudaMalloc(&dy, (size_t)nrows * sizeof(float)));
+  const unsigned g = (unsigned)((nrows * h->P + 255) / 256);
+  if (h->mode == LRB_MODE_FP32)
+    export_rows_kernel<float><<<g, 256, 0, h->stream>>>((const float*)h->X, h->y, row0, nrows, h->p, h->P, dX, dy);
+  else
+    export_rows_kernel<double><<<g, 256, 0, h->stream>>>((const double*)h->X, h->y, row0, nrows, h->p, h->P, dX, dy);
+  h->kernel_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(X_out, dX, (size_t)nrows * h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y_out, dy, (size_t)nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dX); cudaFree(dy);
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "copy_rows failed: %s", cudaGetErrorString(e));
+  return LRB_OK;
+}
+
+// ============================================================ evaluation
+extern "C" int lrb_eval_device(lrb_handle* h, const double* d_beta, double* d_out, int want_grad) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "lrb_eval before lrb_bind_data / lrb_gen_synthetic");
+  if (!d_beta) return fail(h, LRB_E_BAD_ARG, "d_beta is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  int rc = enqueue_eval(h, d_beta, nullptr, want_grad != 0);
+  if (rc) return rc;
+  if (d_out && d_out != h->res)
+    CK(h, cudaMemcpyAsync(d_out, h->res, (size_t)(h->p + 3) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return LRB_OK;
+}
+
+extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad, double* lpost,
+                        double* ll, double* glp) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "lrb_eval before lrb_bind_data / lrb_gen_synthetic");
+  if (!beta || C < 1) return fail(h, LRB_E_BAD_ARG, "beta is NULL or C < 1");
+  if (use_device(h)) return LRB_E_CUDA;
+  const int p = h->p;
+  for (int c = 0; c < C; ++c) {
+    std::memcpy(h->pinned, beta + (size_t)c * p, p * sizeof(double));
+    CK(h, cudaMemcpyAsync(h->beta, h->pinned, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = enqueue_eval(h, h->beta, nullptr, want_grad != 0);
+    if (rc) return rc;
+    double* back = h->pinned + kMaxP;
+    CK(h, cudaMemcpyAsync(back, h->res, (size_t)(p + 3) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (lpost) lpost[c] = back[0];
+    if (ll) ll[c] = back[1];
+    if (glp && want_grad) std::memcpy(glp + (size_t)c * p, back + 3, p * sizeof(double));
+  }
+  return LRB_OK;
+}
+
+extern "C" int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "lrb_lprior before lrb_bind_data / lrb_gen_synthetic");
+  if (!beta || !out || C < 1) return fail(h, LRB_E_BAD_ARG, "bad arguments");
+  if (use_device(h)) return LRB_E_CUDA;
+  double *db = nullptr, *dout = nullptr;
+  CK(h, cudaMalloc(&db, (size_t)C * h->p * sizeof(double)));
+  CK(h, cudaMalloc(&dout, (size_t)C * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(db, beta, (size_t)C * h->p * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    prior_kernel<<<C, kBlock, 0, h->stream>>>(db, h->d_pscale, h->d_logps, h->p, dout);
+    h->kernel_launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(db); cudaFree(dout);
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "lprior failed: %s", cudaGetErrorString(e));
+  return LRB_OK;
+}
+
+// ============================================================ samplers
+namespace {
+
+long long evals_per_step(int kind, int l) { return kind == LRB_HMC ? (long long)l : 1; }
+
+int grow(lrb_handle* h, double** buf, size_t* cap, size_t need) {
+  if (need <= *cap) return LRB_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  CK(h, cudaMalloc(buf, need * sizeof(double)));
+  *cap = need;
+  return LRB_OK;
+}
+
+// capture `nodes` consecutive evaluations into an executable graph
+int build_graph(lrb_handle* h, int nodes, bool want_grad) {
+  if (h->gexec && h->graph_nodes == nodes && h->graph_grad == want_grad) return LRB_OK;
+  drop_graph(h);
+  const long long kl = h->kernel_launches, el = h->eval_launches;
+  CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = LRB_OK;
+  for (int i = 0; i < nodes && rc == LRB_OK; ++i) rc = enqueue_eval(h, h->state->beta_in, h->state, want_grad);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->kernel_launches = kl; h->eval_launches = el;  // capture does not execute
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  h->graph = g;
+  CK(h, cudaGraphInstantiate(&h->gexec, h->graph, 0));
+  h->graph_nodes = nodes;
+  h->graph_grad = want_grad;
+  return LRB_OK;
+}
+
+}  // namespace
+
+extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, const double* init,
+                             int64_t thin, int64_t iters, const double* replay_z, const double* replay_u) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "lrb_run before lrb_bind_data / lrb_gen_synthetic");
+  if (!params || !params->scale) return fail(h, LRB_E_BAD_ARG, "params / params->scale is NULL");
+  const int kind = params->sampler;
+  if (kind < LRB_RWMH || kind > LRB_HMC) return fail(h, LRB_E_BAD_ARG, "unknown sampler %d", kind);
+  if (thin < 1 || iters < 0) return fail(h, LRB_E_BAD_ARG, "thin must be >= 1 and iters >= 0");
+  if (kind == LRB_HMC && params->l < 1) return fail(h, LRB_E_BAD_ARG, "HMC needs l >= 1");
+  if (kind != LRB_RWMH && !(params->step > 0.0)) return fail(h, LRB_E_BAD_ARG, "step (dt / eps) must be > 0");
+  if (params->rng != LRB_RNG_PHILOX && params->rng != LRB_RNG_REPLAY) return fail(h, LRB_E_BAD_ARG, "bad rng %d", params->rng);
+  if (params->rng == LRB_RNG_REPLAY && (!replay_z || (kind != LRB_UL && !replay_u)))
+    return fail(h, LRB_E_BAD_ARG, "replay rng needs replay_z (and replay_u unless UL)");
+  if (!init && (!h->chain_live || h->chain_kind != kind))
+    return fail(h, LRB_E_STATE, "init is NULL but there is no paused chain of this sampler to continue");
+  for (int j = 0; j < h->p; ++j)
+    if (!(params->scale[j] > 0.0)) return fail(h, LRB_E_BAD_ARG, "scale[%d] must be > 0", j);
+  if (use_device(h)) return LRB_E_CUDA;
+
+  const int p = h->p;
+  const long long steps = thin * iters;
+  int rc;
+  if ((rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)iters * p)))) return rc;
+  const double *dz = nullptr, *du = nullptr;
+  if (params->rng == LRB_RNG_REPLAY && steps > 0) {
+    if ((rc = grow(h, &h->d_z, &h->z_cap, (size_t)steps * p))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_z, replay_z, (size_t)steps * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dz = h->d_z;
+    if (kind != LRB_UL) {
+      if ((rc = grow(h, &h->d_u, &h->u_cap, (size_t)steps))) return rc;
+      CK(h, cudaMemcpyAsync(h->d_u, replay_u, (size_t)steps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      du = h->d_u;
+    }
+  }
+  h->run_scale.assign(params->scale, params->scale + p);
+  h->run_params = *params;
+  h->run_params.scale = nullptr;
+  std::memcpy(h->pinned, params->scale, p * sizeof(double));
+  CK(h, cudaMemcpyAsync(h->d_scale, h->pinned, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (init) {
+    std::memcpy(h->pinned + kMaxP, init, p * sizeof(double));
+    CK(h, cudaMemcpyAsync(h->d_init, h->pinned + kMaxP, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  sampler_begin_kernel<<<1, kBlock, 0, h->stream>>>(h->state, init ? h->d_init : nullptr, h->d_scale, kind,
+                                                    params->l, p, params->rng, params->step, params->seed,
+                                                    params->init_lpost, steps, thin, dz, du, h->d_out);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the caller's next call
+
+  h->run_kind = kind;
+  h->run_l = kind == LRB_HMC ? params->l : 1;
+  h->run_want_grad = kind != LRB_RWMH;
+  h->run_thin = thin;
+  h->run_iters = iters;
+  h->pending_init_eval = init != nullptr && (kind == LRB_MALA || kind == LRB_HMC) && steps > 0;
+  h->run_dz = dz;
+  h->run_du = du;
+  h->run_consumed = false;
+  h->run_armed = true;
+  h->chain_live = true;
+  h->chain_kind = kind;
+  return LRB_OK;
+}
+
+extern "C" int lrb_run_evals_per_launch(const lrb_handle* h, int64_t* evals) {
+  if (!h || !evals) return fail(nullptr, LRB_E_BAD_ARG, "NULL argument");
+  if (!h->run_armed) return fail(nullptr, LRB_E_STATE, "no run armed");
+  *evals = h->run_thin * h->run_iters * evals_per_step(h->run_kind, h->run_l);
+  return LRB_OK;
+}
+
+extern "C" int lrb_run_launch(lrb_handle* h) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->run_armed) return fail(h, LRB_E_STATE, "lrb_run_launch before lrb_run_begin");
+  if (use_device(h)) return LRB_E_CUDA;
+  const long long steps = h->run_thin * h->run_iters;
+  if (steps == 0) return LRB_OK;
+  if (h->run_consumed) {
+    // A repeated launch continues the chain: re-arm the window [t, t+steps) and
+    // propose from the paused state (replayed draws, if any, start over).
+    sampler_begin_kernel<<<1, kBlock, 0, h->stream>>>(h->state, nullptr, h->d_scale, h->run_kind,
+                                                      h->run_params.l, h->p, h->run_params.rng,
+                                                      h->run_params.step, h->run_params.seed, 0.0, steps,
+                                                      h->run_thin, h->run_dz, h->run_du, h->d_out);
+    CK(h, cudaGetLastError());
+    h->kernel_launches++;
+  }
+  h->run_consumed = true;
+  long long needed = steps * evals_per_step(h->run_kind, h->run_l) + (h->pending_init_eval ? 1 : 0);
+  h->pending_init_eval = false;
+  // graph of up to 64 evaluations, replayed; the remainder goes out as plain launches
+  const int nodes = (int)std::min<long long>(64, needed);
+  int rc = build_graph(h, nodes, h->run_want_grad);
+  if (rc) return rc;
+  while (needed >= nodes) {
+    CK(h, cudaGraphLaunch(h->gexec, h->stream));
+    const long long per = (h->comm == 1 && h->world > 1) ? 2 : 1;
+    h->kernel_launches += per * nodes;
+    h->eval_launches += nodes;
+    needed -= nodes;
+  }
+  for (; needed > 0; --needed) {
+    rc = enqueue_eval(h, h->state->beta_in, h->state, h->run_want_grad);
+    if (rc) return rc;
+  }
+  return LRB_OK;
+}
+
+extern "C" int lrb_run_finish(lrb_handle* h, double* out, int64_t* accepted) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->run_armed) return fail(h, LRB_E_STATE, "lrb_run_finish before lrb_run_begin");
+  if (use_device(h)) return LRB_E_CUDA;
+  const size_t cnt = (size_t)h->run_iters * h->p;
+  if (out && cnt) CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  long long acc = 0; int phase = -1;
+  CK(h, cudaMemcpyAsync(&acc, &h->state->accepted, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&phase, &h->state->phase, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (accepted) *accepted = acc;
+  if (phase != PH_PAUSED)
+    return fail(h, LRB_E_STATE, "sampler did not reach the end of the run (phase %d): launch count mismatch", phase);
+  return LRB_OK;
+}
+
+extern "C" int lrb_chain_state(lrb_handle* h, double* x, double* lpost, int64_t* steps) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->chain_live) return fail(h, LRB_E_STATE, "no chain has been run on this handle");
+  if (use_device(h)) return LRB_E_CUDA;
+  long long t = 0; double lp = 0.0;
+  if (x) CK(h, cudaMemcpyAsync(x, h->state->x, h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&lp, &h->state->lp_x, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&t, &h->state->t, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (lpost) *lpost = lp;
+  if (steps) *steps = t;
+  return LRB_OK;
+}
+
+extern "C" int lrb_run(lrb_handle* h, const lrb_sampler_params* params, const double* init, int C,
+                       int64_t thin, int64_t iters, const double* replay_z, const double* replay_u,
+                       double* out, int64_t* accepted) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (C < 1) return fail(h, LRB_E_BAD_ARG, "C must be >= 1");
+  if (C > 1 && !init) return fail(h, LRB_E_BAD_ARG, "continuing (init == NULL) is supported for C == 1 only");
+  const int p = h->p;
+  const size_t steps = (size_t)(thin * iters);
+  for (int c = 0; c < C; ++c) {
+    lrb_sampler_params pc = *params;
+    pc.seed = params->seed + (uint64_t)c * 0x9E3779B97F4A7C15ull;  // independent Philox key per chain
+    int rc = lrb_run_begin(h, &pc, init ? init + (size_t)c * p : nullptr, thin, iters,
+                           replay_z ? replay_z + (size_t)c * steps * p : nullptr,
+                           replay_u ? replay_u + (size_t)c * steps : nullptr);
+    if (rc) return rc;
+    if ((rc = lrb_run_launch(h))) return rc;
+    int64_t acc0 = 0;
+    if ((rc = lrb_run_finish(h, out ? out + (size_t)c * iters * p : nullptr, &acc0))) return rc;
+    if (accepted) accepted[c] = acc0;
+  }
+  return LRB_OK;
+}
+
+extern "C" int lrb_rng_dump(lrb_handle* h, uint64_t seed, int64_t t0, int64_t count, int p,
+                            double* z_out, double* u_out) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (count < 1 || p < 1 || !z_out || !u_out) return fail(h, LRB_E_BAD_ARG, "bad arguments");
+  if (use_device(h)) return LRB_E_CUDA;
+  double *dz = nullptr, *du = nullptr;
+  CK(h, cudaMalloc(&dz, (size_t)count * p * sizeof(double)));
+  CK(h, cudaMalloc(&du, (size_t)count * sizeof(double)));
+  rng_dump_kernel<<<(unsigned)((count * p + 255) / 256), 256, 0, h->stream>>>(seed, t0, count, p, dz, du);
+  h->kernel_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(z_out, dz, (size_t)count * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_out, du, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dz); cudaFree(du);
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "rng_dump failed: %s", cudaGetErrorString(e));
+  return LRB_OK;
+}
+
+// ============================================================ communicators
+extern "C" int lrb_nccl_unique_id(void* id_out, const char* libnccl_path) {
+  if (!id_out) return fail(nullptr, LRB_E_BAD_ARG, "id_out is NULL");
+  std::string err;
+  if (!load_nccl(libnccl_path, err)) return fail(nullptr, LRB_E_NCCL, "%s", err.c_str());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  CKN(nullptr, g_nccl.GetUniqueId(&id));
+  std::memcpy(id_out, &id, sizeof id);
+  return LRB_OK;
+}
+
+extern "C" int lrb_comm_init_nccl(lrb_handle* h, int rank, int world, const void* unique_id,
+                                  const char* libnccl_path) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(h, LRB_E_BAD_ARG, "bad rank/world %d/%d", rank, world);
+  if (!unique_id) return fail(h, LRB_E_BAD_ARG, "unique_id is NULL");
+  std::string err;
+  if (!load_nccl(libnccl_path, err)) return fail(h, LRB_E_NCCL, "%s", err.c_str());
+  if (use_device(h)) return LRB_E_CUDA;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof id);
+  CKN(h, g_nccl.CommInitRank(&h->nccl, world, id, rank));
+  h->world = world; h->rank = rank; h->comm = 1;
+  drop_graph(h);
+  return LRB_OK;
+}
+
+extern "C" int lrb_comm_p2p_export(lrb_handle* h, void* ipc_out) {
+  if (!h || !ipc_out) return fail(h, LRB_E_BAD_ARG, "NULL argument");
+  if (use_device(h)) return LRB_E_CUDA;
+  if (!h->mailbox) {
+    CK(h, cudaMalloc(&h->mailbox, kMailBytes));
+    CK(h, cudaMemset(h->mailbox, 0, kMailBytes));
+    h->flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->mailbox) + kMailDoubles * sizeof(double));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t mh;
+  CK(h, cudaIpcGetMemHandle(&mh, h->mailbox));
+  std::memcpy(ipc_out, &mh, sizeof mh);
+  return LRB_OK;
+}
+
+extern "C" int lrb_comm_p2p_connect(lrb_handle* h, int rank, int world, const void* all_handles) {
+  if (!h || !all_handles) return fail(h, LRB_E_BAD_ARG, "NULL argument");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(h, LRB_E_BAD_ARG, "bad rank/world %d/%d", rank, world);
+  if (!h->mailbox) return fail(h, LRB_E_STATE, "call lrb_comm_p2p_export first");
+  if (use_device(h)) return LRB_E_CUDA;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->peer_base[r] = h->mailbox; continue; }
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, (const char*)all_handles + (size_t)r * sizeof mh, sizeof mh);
+    void* base = nullptr;
+    CK(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[r] = base;
+    h->peer_open[r] = true;
+  }
+  CK(h, cudaMemset(h->seq, 0, sizeof(unsigned long long)));
+  h->world = world; h->rank = rank; h->comm = 2;
+  drop_graph(h);
+  return LRB_OK;
+}

@@ -1,0 +1,210 @@
+"""GPU parity of the fused lpost/glp kernel against the oracle and the golden
+fixtures (outputs of the reference's own functions). All calls go through the C ABI
+(ctypes) of liblogreg_b200.so.
+
+Tolerances (BASELINE.json north_star): 1e-10 relative in FP64 mode, 1e-5 in FP32
+mode. lpost/ll are compared relative to their own magnitude; glp relative to the
+un-cancelled gradient magnitude max_j(|X|'|y-p| + |b/v|)_j (SURVEY.md section 7 hard
+part 3: glp -> 0 at the mode, so component-wise relative error is meaningless).
+"""
+import numpy as np
+import pytest
+
+from conftest import ungrad_scale
+from oracle import logreg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp64": 1e-10, "fp32": 1e-5}
+
+
+@pytest.fixture(scope="module")
+def lr():
+    import logreg_b200
+    assert logreg_b200.device_count() >= 1
+    return logreg_b200
+
+
+def check_point(prob, tgt, X, y, beta, mode, pscale):
+    lp, l, g = prob.eval(beta)
+    tol = TOL[mode]
+    with np.errstate(over="ignore"):
+        ref_ll = O.stable_ll(X, y, beta)
+        ref_lp = ref_ll + tgt.lprior(beta)
+        ref_g = tgt.glp(beta)
+    assert abs(l - ref_ll) <= tol * max(1.0, abs(ref_ll)), (l, ref_ll)
+    assert abs(lp - ref_lp) <= tol * max(1.0, abs(ref_lp)), (lp, ref_lp)
+    scale = ungrad_scale(X, y, beta, pscale)
+    err = np.max(np.abs(g - ref_g))
+    assert err <= tol * scale, (err, scale)
+    assert abs(prob.lprior(beta) - tgt.lprior(beta)) <= 1e-12 * max(1.0, abs(tgt.lprior(beta)))
+
+
+def test_pima_golden_fp64(lr, pima):
+    prob = lr.Problem().bind_data(np.asfortranarray(pima["X"]), pima["y"], pima["pscale"], mode="fp64")
+    for i, b in enumerate(pima["B"]):
+        lp, l, g = prob.eval(b)
+        assert l == pytest.approx(pima["ll"][i], rel=1e-10)
+        assert lp == pytest.approx(pima["lpost"][i], rel=1e-10)
+        assert prob.lprior(b) == pytest.approx(pima["lprior"][i], rel=1e-12)
+        scale = ungrad_scale(pima["X"], pima["y"], b, pima["pscale"])
+        assert np.max(np.abs(g - pima["glp"][i])) <= 1e-10 * scale
+    # known answers, SURVEY.md appendix B
+    assert prob.ll(np.zeros(8)) == pytest.approx(-138.62943611198904, rel=1e-12)
+    assert prob.lpost(np.zeros(8)) == pytest.approx(-148.28352947062046, rel=1e-12)
+    np.testing.assert_allclose(prob.glp(np.zeros(8)),
+                               [-32.0, -28.0, -2533.0, -2054.0, -669.5, -870.8, -8.7675, -648.0], rtol=1e-12)
+
+
+def test_pima_module_level_api_and_layouts(lr, pima):
+    """The reference's names, bound by bind_data; every host layout gives the same numbers."""
+    X, y = pima["X"], pima["y"]
+    b = pima["B"][1]
+    ref = None
+    for Xv in (np.asfortranarray(X), np.ascontiguousarray(X), np.asfortranarray(X)[::1, :],
+               np.hstack([X, X])[:, :8], np.ascontiguousarray(X).astype(np.float32).astype(np.float64)):
+        lr.bind_data(Xv, y, pima["pscale"])
+        vals = (lr.lpost(b), lr.ll(b), lr.lprior(b), lr.glp(b))
+        if ref is None:
+            ref = vals
+            assert vals[0] == pytest.approx(pima["lpost"][1], rel=1e-10)
+        else:
+            assert vals[0] == ref[0] and vals[1] == ref[1]
+            np.testing.assert_array_equal(vals[3], ref[3])
+    # y as float64 / bool / uint8
+    for yy in (y.astype(np.float64), y.astype(bool), y.astype(np.uint8)):
+        lr.bind_data(X, yy, pima["pscale"])
+        assert lr.lpost(b) == ref[0]
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_synthetic_golden(lr, synth, mode):
+    X32 = synth["X32"]
+    prob = lr.Problem().bind_data(X32, synth["y"], synth["pscale"], mode=mode)
+    Xd = X32.astype(np.float64)
+    tol = TOL[mode]
+    for i, b in enumerate(synth["B"]):
+        lp, l, g = prob.eval(b)
+        assert lp == pytest.approx(synth["lpost"][i], rel=tol)
+        assert l == pytest.approx(synth["ll"][i], rel=tol)
+        scale = ungrad_scale(Xd, synth["y"], b, synth["pscale"])
+        assert np.max(np.abs(g - synth["glp"][i])) <= tol * scale
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+@pytest.mark.parametrize("p", [1, 3, 8, 13, 32, 64, 100, 128, 200, 256])
+def test_shapes_against_oracle(lr, mode, p):
+    """Ragged sizes: every padded width, row counts around the batch / grid boundaries."""
+    rs = np.random.RandomState(1000 + p)
+    for n in (1, 7, 200, 1031, 4099, 20011):
+        X = rs.randn(n, p).astype(np.float32).astype(np.float64)
+        X[:, 0] = 1.0
+        beta = rs.randn(p) / np.sqrt(p)
+        y = (rs.rand(n) < 1 / (1 + np.exp(-X.dot(beta)))).astype(np.float32)
+        pscale = 0.5 + rs.rand(p) * 3
+        prob = lr.Problem().bind_data(X, y, pscale, mode=mode)
+        tgt = O.Target(X, y, pscale)
+        for b in (beta, np.zeros(p), beta + 0.3 * rs.randn(p)):
+            check_point(prob, tgt, X, y, b, mode, pscale)
+        prob.close()
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_extreme_eta_is_finite(lr, pima, mode):
+    """The reference's naive log(1+exp(.)) overflows to -inf (SURVEY.md hard part 8);
+    the kernel's softplus stays finite and equals the overflow-free value."""
+    prob = lr.Problem().bind_data(pima["X"], pima["y"], pima["pscale"], mode=mode)
+    b = 50.0 * np.ones(8)
+    lp, l, g = prob.eval(b)
+    assert np.isfinite(lp) and np.all(np.isfinite(g))
+    assert l == pytest.approx(O.stable_ll(pima["X"], pima["y"], b), rel=TOL[mode])
+    with np.errstate(over="ignore"):
+        ref_g = O.Target(pima["X"], pima["y"], pima["pscale"]).glp(b)
+    assert np.max(np.abs(g - ref_g)) <= TOL[mode] * ungrad_scale(pima["X"], pima["y"], b, pima["pscale"])
+
+
+def test_eval_many_and_nograd(lr, synth):
+    prob = lr.Problem().bind_data(synth["X32"], synth["y"], synth["pscale"], mode="fp64")
+    lp, l, g = prob.eval_many(synth["B"])
+    np.testing.assert_allclose(lp, synth["lpost"], rtol=1e-10)
+    lp2, l2, g2 = prob.eval_many(synth["B"], want_grad=False)
+    assert g2 is None
+    np.testing.assert_allclose(lp2, lp, rtol=1e-13)
+    # deterministic: same launch configuration => identical bits
+    lp3, _, g3 = prob.eval_many(synth["B"])
+    np.testing.assert_array_equal(lp3, lp)
+    np.testing.assert_array_equal(g3, g)
+
+
+def test_errors(lr, pima):
+    prob = lr.Problem()
+    with pytest.raises(lr.LogregB200Error):
+        prob._ck(prob._lib.lrb_eval(prob._h, None, 1, 1, None, None, None))  # nothing bound
+    with pytest.raises(lr.LogregB200Error, match="0 and 1"):
+        prob.bind_data(pima["X"], pima["y"] + 0.5, pima["pscale"])
+    with pytest.raises(lr.LogregB200Error, match="exceeds"):
+        prob.bind_data(np.ones((4, 300)), np.zeros(4, dtype=np.float32))
+    with pytest.raises(lr.LogregB200Error, match="pscale"):
+        prob.bind_data(pima["X"], pima["y"], -np.ones(8))
+    prob.bind_data(pima["X"], pima["y"], pima["pscale"])
+    with pytest.raises(ValueError):
+        prob.eval(np.zeros(7))
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_synthetic_device_data_against_oracle(lr, mode):
+    """gen_synthetic -> copy_rows -> oracle on the same rows; shards regenerate their rows."""
+    n, p = 300_007, 64
+    prob = lr.Problem()
+    bt = prob.gen_synthetic(n, p, mode=mode, seed=42)
+    X, y = prob.copy_rows(0, n)
+    assert np.all(X[:, 0] == 1.0) and set(np.unique(y)) <= {0.0, 1.0}
+    assert abs(X[:, 1:].mean()) < 0.01 and abs(X[:, 1:].std() - 1) < 0.01
+    assert abs(y.mean() - (1 / (1 + np.exp(-X.dot(bt)))).mean()) < 0.01
+    tgt = O.Target(X, y, prob.pscale)
+    rs = np.random.RandomState(43)
+    for b in (bt, bt + 0.01 * rs.randn(p), np.zeros(p)):
+        check_point(prob, tgt, X, y, b, mode, prob.pscale)
+    # row shards: same global rows, partial sums add up (the multi-GPU decomposition)
+    lo = 123_457
+    a, c = lr.Problem(), lr.Problem()
+    a.gen_synthetic(lo, p, mode=mode, seed=42, beta_true=bt, row_offset=0)
+    c.gen_synthetic(n - lo, p, mode=mode, seed=42, beta_true=bt, row_offset=lo)
+    Xc, yc = c.copy_rows(0, 50)
+    np.testing.assert_array_equal(Xc, X[lo:lo + 50])
+    np.testing.assert_array_equal(yc, y[lo:lo + 50])
+    lp, l, g = prob.eval(bt)
+    lpa, la, ga = a.eval(bt)
+    lpc, lc, gc = c.eval(bt)
+    assert la + lc == pytest.approx(l, rel=1e-12)
+    prior_g = -bt / prob.pscale ** 2
+    np.testing.assert_allclose((ga - prior_g) + (gc - prior_g) + prior_g, g, rtol=1e-9, atol=1e-7)
+
+
+def test_full_size_properties():
+    """BASELINE config 3 shape (n=1e8, p=64, fp32 X = 25.6 GB): size-independent properties.
+    ll(0) = -n log 2 exactly; glp(0)[0] = #ones - n/2; fp32-mode values agree with the sum of
+    four independently generated row shards."""
+    import logreg_b200 as lr
+    n, p = 100_000_000, 64
+    prob = lr.Problem()
+    bt = prob.gen_synthetic(n, p, mode="fp32", seed=42)
+    z = np.zeros(p)
+    lp, l, g = prob.eval(z)
+    assert l == pytest.approx(-n * np.log(2.0), rel=1e-12)
+    lp_t, l_t, g_t = prob.eval(bt)
+    tot_l, tot_g, ones = 0.0, np.zeros(p), 0.0
+    q = n // 4
+    for r in range(4):
+        sh = lr.Problem()
+        sh.gen_synthetic(q, p, mode="fp32", seed=42, beta_true=bt, row_offset=r * q)
+        _, ls, gs = sh.eval(bt)
+        tot_l += ls
+        tot_g += gs + bt / sh.pscale ** 2
+        _, _, g0 = sh.eval(z)
+        ones += g0[0] + q / 2
+        sh.close()
+    assert g[0] == pytest.approx(ones - n / 2, abs=1e-6)
+    assert tot_l == pytest.approx(l_t, rel=1e-11)
+    scale = np.max(np.abs(tot_g)) + 1.0
+    assert np.max(np.abs((tot_g - bt / prob.pscale ** 2) - g_t)) <= 1e-9 * max(scale, np.sqrt(n))
