@@ -1,0 +1,68 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/logreg_b200.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "logreg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from logreg_b200 import _native as N
+    lib = N.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    # the ctypes table covers the header exactly (nothing bound that is not declared, and vice versa)
+    assert sorted(N.SIGNATURES) == names
+    assert lib.lrb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from logreg_b200 import _native as N
+    # lrb_sampler_params: int32 int32 double ptr uint64 int32 int32 double = 48 bytes on LP64
+    assert C.sizeof(N.SamplerParams) == 48
+    assert N.SamplerParams.scale.offset == 16 and N.SamplerParams.init_lpost.offset == 40
+    # lrb_info: int64 + 8*int32 + 3*int64 = 64 bytes
+    assert C.sizeof(N.Info) == 64 and N.Info.bytes_per_eval.offset == 40
+
+
+def test_no_gpu_means_loud_failure():
+    """On a box without a CUDA device the product path must raise, not fall back."""
+    import logreg_b200 as lr
+    from logreg_b200 import _native as N
+    try:
+        have = N.device_count() > 0
+    except lr.LogregB200Error as e:
+        have = False
+        assert e.code == N.E_NO_DEVICE
+        assert "no CPU fallback" in str(e)
+    if have:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lr.LogregB200Error):
+        lr.Problem(0)
+    with pytest.raises(lr.LogregB200Error):
+        lr.bind_data(np.ones((4, 2)), np.zeros(4, dtype=np.float32))
+    with pytest.raises(lr.LogregB200Error, match="bind_data"):
+        lr.use(None)
+        lr.lpost(np.zeros(2))
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under logreg_b200/ may import or call it."""
+    pkg = os.path.join(ROOT, "logreg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("# oracle", ""), os.path.join(dirpath, f)

@@ -10,7 +10,7 @@ part 3: glp -> 0 at the mode, so component-wise relative error is meaningless).
 import numpy as np
 import pytest
 
-from conftest import ungrad_scale
+from tests.helpers import ungrad_scale
 from oracle import logreg_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -62,7 +62,7 @@ def test_pima_module_level_api_and_layouts(lr, pima):
     b = pima["B"][1]
     ref = None
     for Xv in (np.asfortranarray(X), np.ascontiguousarray(X), np.asfortranarray(X)[::1, :],
-               np.hstack([X, X])[:, :8], np.ascontiguousarray(X).astype(np.float32).astype(np.float64)):
+               np.hstack([X, X])[:, :8], np.asfortranarray(np.vstack([X, X]))[:200, :]):
         lr.bind_data(Xv, y, pima["pscale"])
         vals = (lr.lpost(b), lr.ll(b), lr.lprior(b), lr.glp(b))
         if ref is None:
@@ -176,9 +176,12 @@ def test_synthetic_device_data_against_oracle(lr, mode):
     lp, l, g = prob.eval(bt)
     lpa, la, ga = a.eval(bt)
     lpc, lc, gc = c.eval(bt)
-    assert la + lc == pytest.approx(l, rel=1e-12)
+    # FP64: only the order of the float64 adds differs. FP32: the shard boundary is not a
+    # multiple of the 32-row batch, so the float32 per-batch partials differ too.
+    assert la + lc == pytest.approx(l, rel=1e-12 if mode == "fp64" else 1e-6)
     prior_g = -bt / prob.pscale ** 2
-    np.testing.assert_allclose((ga - prior_g) + (gc - prior_g) + prior_g, g, rtol=1e-9, atol=1e-7)
+    gtol = (1e-10 if mode == "fp64" else 1e-5) * ungrad_scale(X, y, bt, prob.pscale)
+    assert np.max(np.abs((ga - prior_g) + (gc - prior_g) + prior_g - g)) <= gtol
 
 
 def test_full_size_properties():
@@ -191,7 +194,9 @@ def test_full_size_properties():
     bt = prob.gen_synthetic(n, p, mode="fp32", seed=42)
     z = np.zeros(p)
     lp, l, g = prob.eval(z)
-    assert l == pytest.approx(-n * np.log(2.0), rel=1e-12)
+    # every row contributes float32(log1pf(1)) = log 2 * (1 + 2.7e-9): the float32 rounding of
+    # the per-row term is coherent in this degenerate case -- the FP32-mode tolerance is 1e-5
+    assert l == pytest.approx(-n * np.log(2.0), rel=1e-7)
     lp_t, l_t, g_t = prob.eval(bt)
     tot_l, tot_g, ones = 0.0, np.zeros(p), 0.0
     q = n // 4
