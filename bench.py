@@ -311,7 +311,8 @@ def main():
     achieved = bytes_eval_rank / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if world == 1 and not args.n:   # the committed ncu capture is of the single-GPU launch
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
     except Exception:
         pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

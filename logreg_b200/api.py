@@ -222,6 +222,31 @@ class Problem:
         self._cache_key = None
         return out, acc.value
 
+    def run_chains(self, kernel, inits, thin, iters, Z=None, U=None, seed=0, init_lpost=-np.inf):
+        """C chains in lock-step on the device (lrb_run with C > 1): inits (C, p) -> samples
+        (C, iters, p) and accepted counts (C,). Chain c uses Philox key seed + c*0x9E3779B97F4A7C15
+        (mod 2^64), or rows of Z (C, thin*iters, p) / U (C, thin*iters) in replay mode."""
+        inits = np.ascontiguousarray(inits, dtype=np.float64)
+        if inits.ndim != 2 or inits.shape[1] != self.p:
+            raise ValueError(f"inits must have shape (C, {self.p})")
+        c = inits.shape[0]
+        rng = N.RNG_REPLAY if Z is not None else N.RNG_PHILOX
+        sp = self._params(kernel, seed, rng, init_lpost)
+        out = np.empty((c, int(iters), self.p))
+        acc = np.zeros(c, dtype=np.int64)
+        if Z is not None:
+            Z = np.ascontiguousarray(Z, dtype=np.float64)
+            if Z.shape != (c, thin * iters, self.p):
+                raise ValueError(f"Z must have shape ({c}, {thin * iters}, {self.p})")
+        if U is not None:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+        self._ck(self._lib.lrb_run(
+            self._h, C.byref(sp), N.as_dp(inits), c, int(thin), int(iters),
+            None if Z is None else N.as_dp(Z), None if U is None else N.as_dp(U),
+            N.as_dp(out), acc.ctypes.data_as(C.POINTER(C.c_int64))))
+        self._cache_key = None
+        return out, acc
+
     def chain_state(self):
         x = np.empty(self.p)
         lp, t = C.c_double(), C.c_int64()

@@ -17,6 +17,7 @@
 #include "../../include/logreg_b200.h"
 #include "data.cuh"
 #include "eval_kernel.cuh"
+#include "eval_mc_kernel.cuh"
 #include "sampler.cuh"
 
 using namespace lrb;
@@ -62,9 +63,12 @@ bool load_nccl(const char* path, std::string& err) {
 }
 
 using EvalFn = void (*)(const EvalArgs);
+using EvalMcFn = void (*)(const EvalMcArgs);
+constexpr int kMcChains = 4;   // chains sharing one X batch in the SIMT many-chain kernel
 
 struct KernelChoice {
   EvalFn grad = nullptr, nograd = nullptr;
+  EvalMcFn mc = nullptr;
   int rows_per_batch = 0;
 };
 
@@ -73,6 +77,7 @@ KernelChoice choice() {
   KernelChoice k;
   k.grad = eval_kernel<T, P, true>;
   k.nograd = eval_kernel<T, P, false>;
+  k.mc = eval_mc_kernel<T, P, kMcChains>;
   k.rows_per_batch = 512 * Chunk<T>::V / P;
   return k;
 }
@@ -156,6 +161,16 @@ struct lrb_handle {
   void* peer_base[kMaxRanks] = {};
   bool peer_open[kMaxRanks] = {};
 
+  // many-chain (C >= 2) state
+  SamplerState* states_mc = nullptr;
+  double* sums_mc = nullptr;   // [C][kSumStride]
+  double* res_mc = nullptr;    // [C][kResStride]
+  double* beta_mc = nullptr;   // [C][kMaxP] staging for host coefficient / init matrices
+  int mc_cap = 0;
+  int run_C = 1, chain_C = 1, graph_C = 1;
+  int grid_mc = 0;
+  long long graph_kl_per_replay = 0, graph_el_per_replay = 0;
+
   long long kernel_launches = 0, eval_launches = 0;
 };
 
@@ -220,6 +235,10 @@ int configure(lrb_handle* h) {
   const long long want = std::max<long long>(1, (nbatch + kWarps - 1) / kWarps);
   h->grid = (int)std::min<long long>((long long)h->sms * occ, want);
   h->grid_nograd = (int)std::min<long long>((long long)h->sms * occ2, want);
+  int occ3 = 0;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, h->kern.mc, kBlock, 0));
+  if (occ3 < 1) return fail(h, LRB_E_CUDA, "many-chain kernel does not fit an SM");
+  h->grid_mc = (int)std::min<long long>((long long)h->sms * occ3, want);
   drop_graph(h);
   h->chain_live = false;
   h->run_armed = false;
@@ -364,7 +383,7 @@ extern "C" int lrb_create(int device, lrb_handle** out) {
   h->stream = h->own_stream;
   CKC(cudaMalloc(&h->d_pscale, kMaxP * sizeof(double)));
   CKC(cudaMalloc(&h->d_logps, kMaxP * sizeof(double)));
-  CKC(cudaMalloc(&h->partials, (size_t)h->sms * 8 * (kMaxP + 1) * sizeof(double)));
+  CKC(cudaMalloc(&h->partials, (size_t)h->sms * 8 * kMcChains * (kMaxP + 1) * sizeof(double)));
   CKC(cudaMalloc(&h->ticket, sizeof(unsigned int)));
   CKC(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
   CKC(cudaMalloc(&h->sums, (kMaxP + 1) * sizeof(double)));
@@ -392,7 +411,8 @@ extern "C" int lrb_destroy(lrb_handle* h) {
     if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   free_data(h);
   void* bufs[] = {h->d_pscale, h->d_logps, h->partials, h->ticket, h->sums, h->res, h->beta, h->d_init,
-                  h->d_scale, h->state, h->seq, h->d_out, h->d_z, h->d_u, h->mailbox};
+                  h->d_scale, h->state, h->seq, h->d_out, h->d_z, h->d_u, h->mailbox,
+                  h->states_mc, h->sums_mc, h->res_mc, h->beta_mc};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -567,6 +587,55 @@ extern "C" int lrb_copy_rows(lrb_handle* h, int64_t row0, int64_t nrows, double*
 }
 
 // ============================================================ evaluation
+namespace {
+
+// states / results / sums for C chains
+int ensure_chains(lrb_handle* h, int C) {
+  if (C <= h->mc_cap) return LRB_OK;
+  if (h->states_mc) cudaFree(h->states_mc);
+  if (h->sums_mc) cudaFree(h->sums_mc);
+  if (h->res_mc) cudaFree(h->res_mc);
+  if (h->beta_mc) cudaFree(h->beta_mc);
+  h->states_mc = nullptr; h->sums_mc = nullptr; h->res_mc = nullptr; h->beta_mc = nullptr; h->mc_cap = 0;
+  CK(h, cudaMalloc(&h->states_mc, (size_t)C * sizeof(SamplerState)));
+  CK(h, cudaMemset(h->states_mc, 0, (size_t)C * sizeof(SamplerState)));
+  CK(h, cudaMalloc(&h->sums_mc, (size_t)C * kSumStride * sizeof(double)));
+  CK(h, cudaMalloc(&h->res_mc, (size_t)C * kResStride * sizeof(double)));
+  CK(h, cudaMalloc(&h->beta_mc, (size_t)C * kMaxP * sizeof(double)));
+  h->mc_cap = C;
+  return LRB_OK;
+}
+
+// Enqueue one fused evaluation of C >= 2 chains: ceil(C/4) passes of the SIMT many-chain
+// kernel (each X batch reused for 4 chains) + one finish launch with a CTA per chain.
+int enqueue_eval_mc(lrb_handle* h, const double* beta_base, long long beta_stride, int C,
+                    SamplerState* states) {
+  constexpr int NC = kMcChains;
+  for (int c0 = 0; c0 < C; c0 += NC) {
+    EvalMcArgs a{};
+    a.X = h->X; a.y = h->y; a.n = h->n;
+    a.partials = h->partials; a.ticket = h->ticket;
+    a.beta_base = beta_base; a.beta_stride = beta_stride;
+    a.chain0 = c0; a.nc_active = std::min(NC, C - c0); a.p = h->p;
+    a.sums = h->sums_mc; a.states = states;
+    h->kern.mc<<<h->grid_mc, kBlock, 0, h->stream>>>(a);
+    CK(h, cudaGetLastError());
+    h->kernel_launches++;
+    h->eval_launches++;
+  }
+  if (h->comm == 1 && h->world > 1)
+    CKN(h, g_nccl.AllReduce(h->sums_mc, h->sums_mc, (size_t)C * kSumStride, ncclDouble, ncclSum, h->nccl, h->stream));
+  FinishArgs f = finish_args(h, nullptr, nullptr);
+  finish_mc_kernel<<<C, kBlock, 0, h->stream>>>(f, h->sums_mc, states, beta_base, beta_stride, h->res_mc);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  return LRB_OK;
+}
+
+bool mc_capable(const lrb_handle* h) { return h->world == 1 || h->comm == 1; }
+
+}  // namespace
+
 extern "C" int lrb_eval_device(lrb_handle* h, const double* d_beta, double* d_out, int want_grad) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
   if (!h->bound) return fail(h, LRB_E_STATE, "lrb_eval before lrb_bind_data / lrb_gen_synthetic");
@@ -586,6 +655,23 @@ extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
   if (!beta || C < 1) return fail(h, LRB_E_BAD_ARG, "beta is NULL or C < 1");
   if (use_device(h)) return LRB_E_CUDA;
   const int p = h->p;
+  if (C >= 2 && mc_capable(h)) {
+    // many-chain path: X is streamed once per 4 chains
+    int rc = ensure_chains(h, C);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->beta_mc, beta, (size_t)C * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = enqueue_eval_mc(h, h->beta_mc, p, C, nullptr))) return rc;
+    std::vector<double> back((size_t)C * kResStride);
+    CK(h, cudaMemcpyAsync(back.data(), h->res_mc, back.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < C; ++c) {
+      const double* r = back.data() + (size_t)c * kResStride;
+      if (lpost) lpost[c] = r[0];
+      if (ll) ll[c] = r[1];
+      if (glp && want_grad) std::memcpy(glp + (size_t)c * p, r + 3, p * sizeof(double));
+    }
+    return LRB_OK;
+  }
   for (int c = 0; c < C; ++c) {
     std::memcpy(h->pinned, beta + (size_t)c * p, p * sizeof(double));
     CK(h, cudaMemcpyAsync(h->beta, h->pinned, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -636,16 +722,28 @@ int grow(lrb_handle* h, double** buf, size_t* cap, size_t need) {
   return LRB_OK;
 }
 
+SamplerState* run_states(lrb_handle* h) { return h->run_C > 1 ? h->states_mc : h->state; }
+
+// one evaluation of every chain of the armed run at its state's beta_in
+int enqueue_run_eval(lrb_handle* h) {
+  if (h->run_C > 1)
+    return enqueue_eval_mc(h, h->states_mc->beta_in, (long long)(sizeof(SamplerState) / sizeof(double)),
+                           h->run_C, h->states_mc);
+  return enqueue_eval(h, h->state->beta_in, h->state, h->run_want_grad);
+}
+
 // capture `nodes` consecutive evaluations into an executable graph
 int build_graph(lrb_handle* h, int nodes, bool want_grad) {
-  if (h->gexec && h->graph_nodes == nodes && h->graph_grad == want_grad) return LRB_OK;
+  if (h->gexec && h->graph_nodes == nodes && h->graph_grad == want_grad && h->graph_C == h->run_C) return LRB_OK;
   drop_graph(h);
   const long long kl = h->kernel_launches, el = h->eval_launches;
   CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int rc = LRB_OK;
-  for (int i = 0; i < nodes && rc == LRB_OK; ++i) rc = enqueue_eval(h, h->state->beta_in, h->state, want_grad);
+  for (int i = 0; i < nodes && rc == LRB_OK; ++i) rc = enqueue_run_eval(h);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->graph_kl_per_replay = h->kernel_launches - kl;
+  h->graph_el_per_replay = h->eval_launches - el;
   h->kernel_launches = kl; h->eval_launches = el;  // capture does not execute
   if (rc) { if (g) cudaGraphDestroy(g); return rc; }
   if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -653,14 +751,12 @@ int build_graph(lrb_handle* h, int nodes, bool want_grad) {
   CK(h, cudaGraphInstantiate(&h->gexec, h->graph, 0));
   h->graph_nodes = nodes;
   h->graph_grad = want_grad;
+  h->graph_C = h->run_C;
   return LRB_OK;
 }
 
-}  // namespace
-
-extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, const double* init,
-                             int64_t thin, int64_t iters, const double* replay_z, const double* replay_u) {
-  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init, int C, int64_t thin,
+            int64_t iters, const double* replay_z, const double* replay_u) {
   if (!h->bound) return fail(h, LRB_E_STATE, "lrb_run before lrb_bind_data / lrb_gen_synthetic");
   if (!params || !params->scale) return fail(h, LRB_E_BAD_ARG, "params / params->scale is NULL");
   const int kind = params->sampler;
@@ -671,7 +767,7 @@ extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, co
   if (params->rng != LRB_RNG_PHILOX && params->rng != LRB_RNG_REPLAY) return fail(h, LRB_E_BAD_ARG, "bad rng %d", params->rng);
   if (params->rng == LRB_RNG_REPLAY && (!replay_z || (kind != LRB_UL && !replay_u)))
     return fail(h, LRB_E_BAD_ARG, "replay rng needs replay_z (and replay_u unless UL)");
-  if (!init && (!h->chain_live || h->chain_kind != kind))
+  if (!init && (!h->chain_live || h->chain_kind != kind || h->chain_C != C))
     return fail(h, LRB_E_STATE, "init is NULL but there is no paused chain of this sampler to continue");
   for (int j = 0; j < h->p; ++j)
     if (!(params->scale[j] > 0.0)) return fail(h, LRB_E_BAD_ARG, "scale[%d] must be > 0", j);
@@ -680,33 +776,41 @@ extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, co
   const int p = h->p;
   const long long steps = thin * iters;
   int rc;
-  if ((rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)iters * p)))) return rc;
+  if (C > 1 && (rc = ensure_chains(h, C))) return rc;
+  if ((rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)C * iters * p)))) return rc;
   const double *dz = nullptr, *du = nullptr;
   if (params->rng == LRB_RNG_REPLAY && steps > 0) {
-    if ((rc = grow(h, &h->d_z, &h->z_cap, (size_t)steps * p))) return rc;
-    CK(h, cudaMemcpyAsync(h->d_z, replay_z, (size_t)steps * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = grow(h, &h->d_z, &h->z_cap, (size_t)C * steps * p))) return rc;
+    CK(h, cudaMemcpyAsync(h->d_z, replay_z, (size_t)C * steps * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     dz = h->d_z;
     if (kind != LRB_UL) {
-      if ((rc = grow(h, &h->d_u, &h->u_cap, (size_t)steps))) return rc;
-      CK(h, cudaMemcpyAsync(h->d_u, replay_u, (size_t)steps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      if ((rc = grow(h, &h->d_u, &h->u_cap, (size_t)C * steps))) return rc;
+      CK(h, cudaMemcpyAsync(h->d_u, replay_u, (size_t)C * steps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       du = h->d_u;
     }
   }
-  h->run_scale.assign(params->scale, params->scale + p);
   h->run_params = *params;
   h->run_params.scale = nullptr;
   std::memcpy(h->pinned, params->scale, p * sizeof(double));
   CK(h, cudaMemcpyAsync(h->d_scale, h->pinned, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const double* d_init = nullptr;
   if (init) {
-    std::memcpy(h->pinned + kMaxP, init, p * sizeof(double));
-    CK(h, cudaMemcpyAsync(h->d_init, h->pinned + kMaxP, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (C == 1) {
+      std::memcpy(h->pinned + kMaxP, init, p * sizeof(double));
+      CK(h, cudaMemcpyAsync(h->d_init, h->pinned + kMaxP, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_init = h->d_init;
+    } else {
+      CK(h, cudaMemcpyAsync(h->beta_mc, init, (size_t)C * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_init = h->beta_mc;
+    }
   }
-  sampler_begin_kernel<<<1, kBlock, 0, h->stream>>>(h->state, init ? h->d_init : nullptr, h->d_scale, kind,
-                                                    params->l, p, params->rng, params->step, params->seed,
+  h->run_C = C;
+  sampler_begin_kernel<<<C, kBlock, 0, h->stream>>>(run_states(h), d_init, h->d_scale, kind, params->l, p,
+                                                    params->rng, params->step, params->seed,
                                                     params->init_lpost, steps, thin, dz, du, h->d_out);
   CK(h, cudaGetLastError());
   h->kernel_launches++;
-  CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the caller's next call
+  CK(h, cudaStreamSynchronize(h->stream));  // staging buffers are reused by the caller's next call
 
   h->run_kind = kind;
   h->run_l = kind == LRB_HMC ? params->l : 1;
@@ -720,18 +824,11 @@ extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, co
   h->run_armed = true;
   h->chain_live = true;
   h->chain_kind = kind;
+  h->chain_C = C;
   return LRB_OK;
 }
 
-extern "C" int lrb_run_evals_per_launch(const lrb_handle* h, int64_t* evals) {
-  if (!h || !evals) return fail(nullptr, LRB_E_BAD_ARG, "NULL argument");
-  if (!h->run_armed) return fail(nullptr, LRB_E_STATE, "no run armed");
-  *evals = h->run_thin * h->run_iters * evals_per_step(h->run_kind, h->run_l);
-  return LRB_OK;
-}
-
-extern "C" int lrb_run_launch(lrb_handle* h) {
-  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+int launch_run(lrb_handle* h) {
   if (!h->run_armed) return fail(h, LRB_E_STATE, "lrb_run_launch before lrb_run_begin");
   if (use_device(h)) return LRB_E_CUDA;
   const long long steps = h->run_thin * h->run_iters;
@@ -739,10 +836,10 @@ extern "C" int lrb_run_launch(lrb_handle* h) {
   if (h->run_consumed) {
     // A repeated launch continues the chain: re-arm the window [t, t+steps) and
     // propose from the paused state (replayed draws, if any, start over).
-    sampler_begin_kernel<<<1, kBlock, 0, h->stream>>>(h->state, nullptr, h->d_scale, h->run_kind,
-                                                      h->run_params.l, h->p, h->run_params.rng,
-                                                      h->run_params.step, h->run_params.seed, 0.0, steps,
-                                                      h->run_thin, h->run_dz, h->run_du, h->d_out);
+    sampler_begin_kernel<<<h->run_C, kBlock, 0, h->stream>>>(run_states(h), nullptr, h->d_scale, h->run_kind,
+                                                             h->run_params.l, h->p, h->run_params.rng,
+                                                             h->run_params.step, h->run_params.seed, 0.0, steps,
+                                                             h->run_thin, h->run_dz, h->run_du, h->d_out);
     CK(h, cudaGetLastError());
     h->kernel_launches++;
   }
@@ -755,32 +852,60 @@ extern "C" int lrb_run_launch(lrb_handle* h) {
   if (rc) return rc;
   while (needed >= nodes) {
     CK(h, cudaGraphLaunch(h->gexec, h->stream));
-    const long long per = (h->comm == 1 && h->world > 1) ? 2 : 1;
-    h->kernel_launches += per * nodes;
-    h->eval_launches += nodes;
+    h->kernel_launches += h->graph_kl_per_replay;
+    h->eval_launches += h->graph_el_per_replay;
     needed -= nodes;
   }
-  for (; needed > 0; --needed) {
-    rc = enqueue_eval(h, h->state->beta_in, h->state, h->run_want_grad);
-    if (rc) return rc;
+  for (; needed > 0; --needed)
+    if ((rc = enqueue_run_eval(h))) return rc;
+  return LRB_OK;
+}
+
+int finish_run(lrb_handle* h, double* out, int64_t* accepted) {
+  if (!h->run_armed) return fail(h, LRB_E_STATE, "lrb_run_finish before lrb_run_begin");
+  if (use_device(h)) return LRB_E_CUDA;
+  const int C = h->run_C;
+  const size_t cnt = (size_t)C * h->run_iters * h->p;
+  if (out && cnt) CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<long long> acc(C, 0);
+  std::vector<int> phase(C, -1);
+  SamplerState* st = run_states(h);
+  CK(h, cudaMemcpy2DAsync(acc.data(), sizeof(long long), &st->accepted, sizeof(SamplerState), sizeof(long long), C,
+                          cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpy2DAsync(phase.data(), sizeof(int), &st->phase, sizeof(SamplerState), sizeof(int), C,
+                          cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < C; ++c) {
+    if (accepted) accepted[c] = acc[c];
+    if (phase[c] != PH_PAUSED)
+      return fail(h, LRB_E_STATE, "chain %d did not reach the end of the run (phase %d): launch count mismatch", c, phase[c]);
   }
   return LRB_OK;
 }
 
+}  // namespace
+
+extern "C" int lrb_run_begin(lrb_handle* h, const lrb_sampler_params* params, const double* init,
+                             int64_t thin, int64_t iters, const double* replay_z, const double* replay_u) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  return arm_run(h, params, init, 1, thin, iters, replay_z, replay_u);
+}
+
+extern "C" int lrb_run_evals_per_launch(const lrb_handle* h, int64_t* evals) {
+  if (!h || !evals) return fail(nullptr, LRB_E_BAD_ARG, "NULL argument");
+  if (!h->run_armed) return fail(nullptr, LRB_E_STATE, "no run armed");
+  *evals = h->run_thin * h->run_iters * evals_per_step(h->run_kind, h->run_l);
+  return LRB_OK;
+}
+
+extern "C" int lrb_run_launch(lrb_handle* h) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  return launch_run(h);
+}
+
 extern "C" int lrb_run_finish(lrb_handle* h, double* out, int64_t* accepted) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
-  if (!h->run_armed) return fail(h, LRB_E_STATE, "lrb_run_finish before lrb_run_begin");
-  if (use_device(h)) return LRB_E_CUDA;
-  const size_t cnt = (size_t)h->run_iters * h->p;
-  if (out && cnt) CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  long long acc = 0; int phase = -1;
-  CK(h, cudaMemcpyAsync(&acc, &h->state->accepted, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(&phase, &h->state->phase, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
-  if (accepted) *accepted = acc;
-  if (phase != PH_PAUSED)
-    return fail(h, LRB_E_STATE, "sampler did not reach the end of the run (phase %d): launch count mismatch", phase);
-  return LRB_OK;
+  return finish_run(h, out, accepted);
 }
 
 extern "C" int lrb_chain_state(lrb_handle* h, double* x, double* lpost, int64_t* steps) {
@@ -788,9 +913,10 @@ extern "C" int lrb_chain_state(lrb_handle* h, double* x, double* lpost, int64_t*
   if (!h->chain_live) return fail(h, LRB_E_STATE, "no chain has been run on this handle");
   if (use_device(h)) return LRB_E_CUDA;
   long long t = 0; double lp = 0.0;
-  if (x) CK(h, cudaMemcpyAsync(x, h->state->x, h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(&lp, &h->state->lp_x, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(&t, &h->state->t, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  SamplerState* st = h->chain_C > 1 ? h->states_mc : h->state;   // chain 0 of a many-chain run
+  if (x) CK(h, cudaMemcpyAsync(x, st->x, h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&lp, &st->lp_x, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&t, &st->t, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   if (lpost) *lpost = lp;
   if (steps) *steps = t;
@@ -802,19 +928,27 @@ extern "C" int lrb_run(lrb_handle* h, const lrb_sampler_params* params, const do
                        double* out, int64_t* accepted) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
   if (C < 1) return fail(h, LRB_E_BAD_ARG, "C must be >= 1");
-  if (C > 1 && !init) return fail(h, LRB_E_BAD_ARG, "continuing (init == NULL) is supported for C == 1 only");
+  if (C == 1 || mc_capable(h)) {
+    // all chains advance in lock-step on the device (many-chain kernel for C >= 2)
+    int rc = arm_run(h, params, init, C, thin, iters, replay_z, replay_u);
+    if (rc) return rc;
+    if ((rc = launch_run(h))) return rc;
+    return finish_run(h, out, accepted);
+  }
+  // row-sharded with the fused peer-memory allreduce: chains one after the other
+  if (!init) return fail(h, LRB_E_BAD_ARG, "continuing (init == NULL) needs C == 1 in this configuration");
   const int p = h->p;
   const size_t steps = (size_t)(thin * iters);
   for (int c = 0; c < C; ++c) {
     lrb_sampler_params pc = *params;
-    pc.seed = params->seed + (uint64_t)c * 0x9E3779B97F4A7C15ull;  // independent Philox key per chain
-    int rc = lrb_run_begin(h, &pc, init ? init + (size_t)c * p : nullptr, thin, iters,
-                           replay_z ? replay_z + (size_t)c * steps * p : nullptr,
-                           replay_u ? replay_u + (size_t)c * steps : nullptr);
+    pc.seed = params->seed + (uint64_t)c * 0x9E3779B97F4A7C15ull;  // the key chain c gets in the lock-step path
+    int rc = arm_run(h, &pc, init + (size_t)c * p, 1, thin, iters,
+                     replay_z ? replay_z + (size_t)c * steps * p : nullptr,
+                     replay_u ? replay_u + (size_t)c * steps : nullptr);
     if (rc) return rc;
-    if ((rc = lrb_run_launch(h))) return rc;
+    if ((rc = launch_run(h))) return rc;
     int64_t acc0 = 0;
-    if ((rc = lrb_run_finish(h, out ? out + (size_t)c * iters * p : nullptr, &acc0))) return rc;
+    if ((rc = finish_run(h, out ? out + (size_t)c * iters * p : nullptr, &acc0))) return rc;
     if (accepted) accepted[c] = acc0;
   }
   return LRB_OK;

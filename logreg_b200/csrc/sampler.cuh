@@ -224,14 +224,19 @@ __device__ inline void sampler_on_eval(SamplerState* st, double lp, double g, do
   if (!last) sampler_propose(st, scratch);
 }
 
-// Arm the state for a run of `steps` kernel applications. init == nullptr
-// continues from the paused chain.  Launched as <<<1, kBlock>>>.
-__global__ void sampler_begin_kernel(SamplerState* st, const double* init, const double* scale,
+// Arm the state(s) for a run of `steps` kernel applications. init == nullptr
+// continues from the paused chain.  Launched as <<<C, kBlock>>>: block c arms chain c
+// (states[c], init + c*p, Philox key seed + c*golden, replay rows c*steps.., samples
+// out + c*iters*p).
+__global__ void sampler_begin_kernel(SamplerState* states, const double* init, const double* scale,
                                      int kind, int l, int p, int rng, double step, uint64_t seed,
                                      double init_lpost, long long steps, long long thin, const double* z,
                                      const double* u, double* out) {
   __shared__ double scratch[kWarps];
   const int j = threadIdx.x;
+  const long long c = blockIdx.x;
+  SamplerState* st = states + c;
+  if (init) init += c * p;
   if (j < p) {
     st->scale[j] = scale[j];
     st->sqrt_scale[j] = sqrt(scale[j]);
@@ -239,13 +244,16 @@ __global__ void sampler_begin_kernel(SamplerState* st, const double* init, const
   }
   if (j == 0) {
     st->kind = kind; st->l = l; st->p = p; st->rng = rng;
-    st->step = step; st->sqrt_step = sqrt(step); st->seed = seed;
+    st->step = step; st->sqrt_step = sqrt(step);
+    st->seed = seed + (uint64_t)c * 0x9E3779B97F4A7C15ull;
     if (init) { st->t = 0; st->accepted = 0; st->lp_x = init_lpost; st->k0 = 0.0; }
     st->t_run0 = st->t;
     st->t_replay0 = st->t;
     st->t_end = st->t + steps;
     st->thin = thin;
-    st->z = z; st->u = u; st->out = out;
+    st->z = z ? z + c * steps * p : nullptr;
+    st->u = u ? u + c * steps : nullptr;
+    st->out = out + c * (steps / thin) * p;
     st->leap = 0;
   }
   __syncthreads();

@@ -278,3 +278,54 @@ def test_device_philox_matches_its_specification(lr, pima):
             r = philox_ref([t & 0xFFFFFFFF, t >> 32, j, 0], key)
             z = np.sqrt(-2.0 * np.log(u53(r[0], r[1]))) * np.cos(2 * np.pi * u53(r[2], r[3]))
             assert Z[i, j] == pytest.approx(z, rel=1e-12, abs=1e-14)
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_many_chain_evaluation_matches_single_chain(lr, synth, mode):
+    """lrb_eval with C >= 2 goes through the many-chain kernel (X batch reused for 4 chains)."""
+    prob = lr.Problem().bind_data(synth["X32"], synth["y"], synth["pscale"], mode=mode)
+    rs = np.random.RandomState(8)
+    for c in (2, 3, 4, 7, 13):
+        B = synth["beta_true"] + 0.2 * rs.randn(c, 32)
+        lp, l, g = prob.eval_many(B)
+        for i in range(c):
+            prob._cache_key = None
+            lp1, l1, g1 = prob.eval(B[i])
+            assert lp[i] == pytest.approx(lp1, rel=1e-13)
+            assert l[i] == pytest.approx(l1, rel=1e-13)
+            np.testing.assert_allclose(g[i], g1, rtol=1e-11, atol=1e-9)
+    Xd = synth["X32"].astype(np.float64)
+    tgt = O.Target(Xd, synth["y"], synth["pscale"])
+    lp, l, g = prob.eval_many(synth["B"])
+    tol = 1e-10 if mode == "fp64" else 1e-5
+    np.testing.assert_allclose(lp, synth["lpost"], rtol=tol)
+
+
+@pytest.mark.parametrize("kind", ["rwmh", "ul", "mala", "hmc_l7"])
+def test_lockstep_chains_equal_independent_runs(lr, pima, kind):
+    """C chains advanced in lock-step by the many-chain kernel == C separate single-chain runs
+    with the same per-chain Philox keys (fp64: identical decisions, states to 1e-9)."""
+    prob = lr.Problem().bind_data(pima["X"], pima["y"], pima["pscale"])
+    k = make_kernel(lr, prob, pima, kind)
+    rs = np.random.RandomState(4)
+    C = 6
+    inits = pima["chain_init"] + 0.01 * rs.randn(C, 8) * np.array([1., .02, .005, .005, .005, .01, .3, .01])
+    seed = 424242
+    mats, accs = prob.run_chains(k, inits, 3, 15, seed=seed)
+    assert mats.shape == (C, 15, 8)
+    for c in range(C):
+        m1, a1 = prob.run(k, inits[c], 3, 15, seed=(seed + c * 0x9E3779B97F4A7C15) % 2 ** 64)
+        assert a1 == accs[c]
+        np.testing.assert_allclose(mats[c], m1, rtol=1e-9, atol=1e-9)
+
+
+def test_lockstep_chains_replay_reference(lr, pima):
+    """Replay mode with per-chain streams: every chain reproduces the reference HMC chain."""
+    prob = lr.Problem().bind_data(np.asfortranarray(pima["X"]), pima["y"], pima["pscale"])
+    k = make_kernel(lr, prob, pima, "hmc_l7")
+    Z, U, ref = pima["hmc_l7_t1_Z"][:60], pima["hmc_l7_t1_U"][:60], pima["hmc_l7_t1_mat"][:60]
+    C = 5
+    mats, accs = prob.run_chains(k, np.tile(pima["chain_init"], (C, 1)), 1, 60,
+                                 Z=np.tile(Z, (C, 1, 1)), U=np.tile(U, (C, 1)))
+    for c in range(C):
+        np.testing.assert_allclose(mats[c], ref, rtol=1e-7, atol=1e-7)

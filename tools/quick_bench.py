@@ -25,7 +25,7 @@ def time_evals(prob, reps=20, grad=True):
     prob.set_stream(None)
     return e0.elapsed_time(e1) / reps
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--latency" not in sys.argv:
     torch.cuda.init()
     for mode, n, p in [("fp32", 20_000_000, 64), ("fp32", 100_000_000, 64), ("fp32", 1_000_000, 32),
                        ("fp64", 20_000_000, 64), ("fp64", 10_000_000, 128), ("fp32", 40_000_000, 32), ("fp32", 20_000_000, 128)]:
@@ -37,3 +37,29 @@ if __name__ == "__main__":
             print(f"{mode} n={n} p={p} grad={grad} grid={inf['grid']} gen={tg:.2f}s  {ms:.4f} ms/eval  "
                   f"{inf['bytes_per_eval'] / ms / 1e6:.1f} GB/s", flush=True)
         prob.close()
+
+
+def latency_probe():
+    """Fixed per-launch cost: tiny n, eval-only loop and sampler (graph) loop."""
+    import numpy as np
+    for mode, n, p in [("fp32", 1000, 64), ("fp32", 100_000, 64), ("fp32", 1_000_000, 32), ("fp32", 1_000_000, 64)]:
+        prob = lr.Problem()
+        bt = prob.gen_synthetic(n, p, mode=mode)
+        ms = time_evals(prob, reps=200)
+        for name, kern in (("hmc", lr.hmcKernel(prob.lpost, prob.glp, eps=1e-4, l=20, dmm=1.0)),
+                           ("mala", lr.malaKernel(prob.lpost, prob.glp, dt=1e-6, pre=1.0)),
+                           ("rwmh", lr.mhKernel(prob.lpost, lr.RandomWalk(1e-4 * np.ones(p))))):
+            prob.run(kern, bt, 1, 50, seed=1)
+            t0 = time.perf_counter(); prob.run(kern, None, 1, 2000 if name != "hmc" else 200, seed=1); dt = time.perf_counter() - t0
+            ev = 2000 if name != "hmc" else 200 * 20
+            print(f"latency {mode} n={n} p={p}: eval-only {ms*1e3:.1f} us | {name} graph loop {dt/ev*1e6:.1f} us/eval", flush=True)
+        # many-chain SIMT kernel
+        for C in (4, 16, 64):
+            B = np.tile(bt, (C, 1))
+            prob.eval_many(B)
+            t0 = time.perf_counter(); prob.eval_many(B); dt = time.perf_counter() - t0
+            print(f"   many-chain C={C}: {dt*1e3:.3f} ms per all-chain eval = {dt/C*1e6:.1f} us/chain-eval (host-timed)", flush=True)
+        prob.close()
+
+if __name__ == "__main__" and "--latency" in sys.argv:
+    latency_probe()
