@@ -148,6 +148,11 @@ int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
  * d_beta: p doubles; d_out: [lpost, ll, lprior, glp[0..p)] = p+3 doubles. */
 int lrb_eval_device(lrb_handle* h, const double* d_beta, double* d_out, int want_grad);
 
+/* Diagnostic for the tensor-core many-chain kernel: runs it on C coefficient vectors and
+ * returns eta = x.beta of the FIRST 128-row tile, eta_out[ceil(C/128)*128][128] (chain-major),
+ * as the tensor cores produced it (3xTF32).  Test instrumentation; not part of the drop-in path. */
+int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float* eta_out);
+
 /* lprior alone (fit-np-ul.py:33-34; no pass over X). beta: C x p host; out: C. */
 int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out);
 

@@ -1,0 +1,432 @@
+// eval_tc_kernel.cuh -- many-chain fused lpost+glp on the 5th-generation tensor
+// cores (tcgen05 + TMEM + TMA), FP32-storage mode, "3xTF32" arithmetic.
+//
+// For C chains the two passes over X become dense contractions (BASELINE.json
+// north_star (b), config 4):
+//     Eta' [chains x rows] = B [chains x p] . X' [p x rows]          (MMA1)
+//     G    [chains x p]    = R [chains x rows] . X [rows x p]        (MMA2)
+// with the link functions (softplus / sigmoid residual) applied element-wise in
+// between, per (chain, row).  Reference arithmetic replaced: ll fit-numpy.py:23-24,
+// glp fit-np-ul.py:45-48, evaluated for 128 chains x 128 rows per tile.
+//
+// One CTA (384 threads, 1 per SM) owns one group of 128 chains and a strided set of
+// 128-row tiles:
+//   warp 0      TMA producer: X tile (P/32 boxes of 128 rows x 32 floats, 128B swizzle)
+//               + the 128 y bytes, 2-stage mbarrier ring.
+//   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
+//   warp 2      TMEM allocator (512 columns).
+//   warps 4-7   epilogue: thread = chain (TMEM lane).  tcgen05.ld eta (32 rows at a
+//               time), link functions, log-likelihood into a per-thread accumulator
+//               (no cross-thread reduction: a thread owns its chain), residual r
+//               rounded to TF32 and written back IN PLACE with tcgen05.st, so MMA2
+//               takes R straight from TMEM as its A operand.
+//   warps 8-11  converters: Xl = X - trunc_tf32(X) into a second smem buffer.
+// Precision (hard part 4): single-pass TF32 cannot meet 1e-5, so
+//   eta = Xh.Bh + Xl.Bh + Xh.Bl   (3 MMAs; the tensor core ignores the 13 low mantissa
+//                                   bits of an fp32 operand, so raw X serves as Xh)
+//   G   = Rh.Xh + Rh.Xl           (R rounded to nearest TF32: unbiased, 2^-12 relative,
+//                                   averaged over >= thousands of rows)
+// and the TMEM (fp32) gradient accumulator is flushed into float64 partial sums in
+// global memory every kFlush tiles (1024 rows).
+//
+// The same smem X tile is the K-major B operand of MMA1 (N = rows, K = p) and the
+// MN-major B operand of MMA2 (N = p, K = rows): no transpose is ever materialised.
+#pragma once
+#include <cuda.h>
+
+#include "eval_mc_kernel.cuh"
+
+namespace lrb {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcRows = 128;     // rows per tile (MMA1 N, MMA2 K)
+constexpr int kTcChains = 128;   // chains per CTA (MMA M)
+constexpr int kFlush = 8;        // tiles between float64 flushes of the TMEM gradient
+
+struct EvalTcArgs {
+  const uint8_t* y;            // n bytes, allocation padded to a multiple of 128
+  long long n;
+  int ntiles;                  // ceil(n / 128)
+  const double* beta_base;     // chain c at beta_base + c*beta_stride (doubles)
+  long long beta_stride;
+  int C;                       // chains
+  int p;
+  double* partials;            // [gridDim.x][gridDim.y][P+1][128]: col 0 = ll, 1+j = gll_j
+  const SamplerState* states;  // pause check (nullptr for a bare evaluation)
+  float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][128]
+};
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32.
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t to_tf32_rna(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+}  // namespace tc
+
+template <int P>
+struct TcLayout {
+  static constexpr int kBoxes = P / 32;                 // 32-float (128-byte) column boxes per tile
+  static constexpr uint32_t kBoxBytes = 128 * 128;      // 128 rows x 128 bytes
+  static constexpr uint32_t kTileBytes = kBoxes * kBoxBytes;   // X tile == beta tile size
+  static constexpr uint32_t kStageBytes = 2 * kTileBytes;      // X + Xl
+  static constexpr uint32_t kOffBh = 2 * kStageBytes;
+  static constexpr uint32_t kOffBl = kOffBh + kTileBytes;
+  static constexpr uint32_t kOffY = kOffBl + kTileBytes;        // 2 x 128 bytes
+  static constexpr uint32_t kOffBar = kOffY + 256;
+  static constexpr uint32_t kNumBar = 14;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBar * 8;
+  static constexpr uint32_t kBytes = kOffTmemPtr + 16;
+  static constexpr uint32_t kDynSmem = kBytes + 1024;           // manual 1024-byte alignment slack
+};
+
+template <int P>
+__global__ void __launch_bounds__(kTcThreads, 1)
+eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
+  using namespace tc;
+  using Lay = TcLayout<P>;
+  static_assert(P == 32 || P == 64, "tensor-core path supports P = 32 or 64");
+  constexpr int KQ = P / 8;            // MMA1 k-chunks (TF32 UMMA_K = 8)
+  constexpr int RQ = kTcRows / 8;      // MMA2 k-chunks
+  // TMEM columns: eta/R double buffer [0,256), gradient accumulator [256, 256+P)
+  constexpr uint32_t kColD1 = 0, kColG = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to the aligned base
+
+  if (a.states != nullptr && a.states[0].phase == PH_PAUSED) return;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cg = blockIdx.y;                       // chain group
+  const int ntiles_mine = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  auto bar = [&](int i) { return base + Lay::kOffBar + 8u * i; };
+  // barrier indices
+  constexpr int X_FULL = 0, XL_FULL = 2, X_EMPTY = 4, D1_FULL = 6, R_FULL = 8, G_FULL = 10, G_FREE = 11;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(X_FULL + s), 1);
+      mbar_init(bar(XL_FULL + s), 128);
+      mbar_init(bar(X_EMPTY + s), 1);
+      mbar_init(bar(D1_FULL + s), 1);
+      mbar_init(bar(R_FULL + s), 128);
+    }
+    mbar_init(bar(G_FULL), 1);
+    mbar_init(bar(G_FREE), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + Lay::kOffTmemPtr), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+
+  // beta tile of this chain group -> smem (K-major, 128-byte swizzle), hi and lo parts
+  for (int idx = tid; idx < kTcChains * P; idx += kTcThreads) {
+    const int c = idx / P, k = idx % P;
+    const int chain = cg * kTcChains + c;
+    double b = 0.0;
+    if (chain < a.C && k < a.p) b = a.beta_base[(long long)chain * a.beta_stride + k];
+    const float bh = trunc_tf32((float)b);
+    const float bl = (float)(b - (double)bh);
+    const int box = k >> 5, kk = k & 31;
+    const uint32_t off = box * Lay::kBoxBytes + c * 128 + ((((uint32_t)kk >> 2) ^ ((uint32_t)c & 7u)) << 4) + (kk & 3) * 4;
+    *reinterpret_cast<float*>(gen + Lay::kOffBh + off) = bh;
+    *reinterpret_cast<float*>(gen + Lay::kOffBl + off) = bl;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + Lay::kOffTmemPtr);
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < ntiles_mine; ++i) {
+        const int s = i & 1;
+        const int tile = blockIdx.x + i * gridDim.x;
+        mbar_wait(bar(X_EMPTY + s), ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(X_FULL + s), Lay::kTileBytes + 128u);
+        const uint32_t dst = base + s * Lay::kStageBytes;
+#pragma unroll
+        for (int b = 0; b < Lay::kBoxes; ++b) tma_load_2d(dst + b * Lay::kBoxBytes, &xmap, bar(X_FULL + s), 32 * b, tile * kTcRows);
+        bulk_load(base + Lay::kOffY + s * 128, a.y + (long long)tile * kTcRows, 128u, bar(X_FULL + s));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (K-major), B = X rows (K-major)
+      constexpr uint32_t idesc2 = instr_desc(kTcChains, P, 0, 1);         // A = R (TMEM), B = X (MN-major)
+      auto issue_mma2 = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(bar(R_FULL + s), (j >> 1) & 1);
+        tc_fence_after();
+        const bool first_of_group = (j % kFlush) == 0;
+        if (first_of_group && j > 0) mbar_wait(bar(G_FREE), ((j / kFlush) - 1) & 1);
+        const uint32_t xs = base + s * Lay::kStageBytes;
+        const uint32_t a_t = tmem + kColD1 + s * kTcRows;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // Rh.Xh then Rh.Xl
+          const uint32_t xb = xs + half * Lay::kTileBytes;
+#pragma unroll
+          for (int q = 0; q < RQ; ++q) {
+            const uint64_t bdesc = smem_desc(xb + q * 1024u, Lay::kBoxBytes, 1024u);
+            mma_ts(tmem + kColG, a_t + q * 8, bdesc, idesc2, (first_of_group && half == 0 && q == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(bar(X_EMPTY + s));                 // stage s (X, Xl, R) is free again
+        if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL));
+      };
+      for (int i = 0; i < ntiles_mine; ++i) {
+        const int s = i & 1;
+        mbar_wait(bar(X_FULL + s), (i >> 1) & 1);
+        mbar_wait(bar(XL_FULL + s), (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t xs = base + s * Lay::kStageBytes;
+        const uint32_t d1 = tmem + kColD1 + s * kTcRows;
+        // eta' = Bh.Xh' + Bh.Xl' + Bl.Xh'
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t ab = base + (term == 2 ? Lay::kOffBl : Lay::kOffBh);
+          const uint32_t xb = xs + (term == 1 ? Lay::kTileBytes : 0u);
+#pragma unroll
+          for (int q = 0; q < KQ; ++q) {
+            const uint32_t koff = (q >> 2) * Lay::kBoxBytes + (q & 3) * 32u;
+            mma_ss(d1, smem_desc(ab + koff, 16u, 1024u), smem_desc(xb + koff, 16u, 1024u), idesc1,
+                   (term == 0 && q == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(bar(D1_FULL + s));
+        if (i > 0) issue_mma2(i - 1);
+      }
+      if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
+    }
+  } else if (warp >= 8) {
+    // ===================== converters: Xl = X - trunc_tf32(X), same (swizzled) offsets
+    const int ct = tid - 256;
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i & 1;
+      mbar_wait(bar(X_FULL + s), (i >> 1) & 1);
+      const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes);
+      float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + Lay::kTileBytes);
+#pragma unroll 4
+      for (int k = ct; k < (int)(Lay::kTileBytes / 16); k += 128) {
+        const float4 x = src[k];
+        float4 l;
+        l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
+        l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
+        dst[k] = l;
+      }
+      fence_async_smem();
+      mbar_arrive(bar(XL_FULL + s));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = chain
+    const int ci = (warp & 3) * 32 + lane;                 // chain within the group == TMEM lane
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+    double ll_acc = 0.0;
+    double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)(P + 1) * kTcChains;
+    bool first_flush = true;
+    int flushes = 0;
+    const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i & 1;
+      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows;
+      const bool full = row0 + kTcRows <= a.n;
+      mbar_wait(bar(D1_FULL + s), (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t* ys = reinterpret_cast<const uint32_t*>(gen + Lay::kOffY + s * 128);
+      float ll_tile = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < kTcRows / 32; ++ch) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + lane_addr + kColD1 + s * kTcRows + ch * 32;
+        tmem_ld32(taddr, v);
+        if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + ch * 32 + k] = __uint_as_float(v[k]);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const uint32_t y4 = ys[ch * 8 + k4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int k = k4 * 4 + kk;
+            const float eta = __uint_as_float(v[k]);
+            const bool y1 = ((y4 >> (8 * kk)) & 0xFFu) != 0u;
+            const float ae = fabsf(eta);
+            const float e = ex2_approx(-ae * LOG2E);
+            const float t = 1.0f + e;
+            const float inv = rcp_approx(t);
+            const float l1p = lg2_approx(t) * LN2;
+            const bool pos = eta >= 0.0f;
+            const float sm = e * inv;
+            const float pr = pos ? inv : sm;               // sigmoid(eta)
+            const float r = y1 ? (pos ? sm : inv) : -pr;   // y - sigmoid(eta), cancellation-free
+            const float z = y1 ? eta : -eta;
+            float lt = fminf(z, 0.0f) - l1p;
+            if (!full && row0 + ch * 32 + k >= a.n) lt = 0.0f;
+            ll_tile += lt;
+            v[k] = to_tf32_rna(r);
+          }
+        }
+        tmem_st32(taddr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar(R_FULL + s));
+      ll_acc += (double)ll_tile;
+
+      if ((i % kFlush) == kFlush - 1 || i == ntiles_mine - 1) {
+        // flush the fp32 TMEM gradient accumulator into float64 partial sums
+        mbar_wait(bar(G_FULL), flushes & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < P / 32; ++ch) {
+          uint32_t g[32];
+          tmem_ld32(tmem + lane_addr + kColG + ch * 32, g);
+          if (ch == P / 32 - 1) { tc_fence_before(); mbar_arrive(bar(G_FREE)); }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            double* dst = part + (size_t)(1 + ch * 32 + k) * kTcChains + ci;
+            const double add = (double)__uint_as_float(g[k]);
+            *dst = first_flush ? add : (*dst + add);
+          }
+        }
+        first_flush = false;
+        ++flushes;
+      }
+    }
+    part[ci] = ll_acc;
+    if (ntiles_mine == 0) {
+      for (int j = 0; j < P; ++j) part[(size_t)(1 + j) * kTcChains + ci] = 0.0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+// One CTA per chain: sum the per-CTA float64 partials over row CTAs in a fixed order,
+// then the common finish (prior, result, sampler update).
+__global__ void finish_tc_kernel(FinishArgs base, const double* partials, int row_ctas, int groups, int P,
+                                 SamplerState* states, const double* beta_base, long long beta_stride,
+                                 double* res) {
+  __shared__ double s_sums[kMaxP + 1];
+  __shared__ double scratch[kWarps];
+  const int c = blockIdx.x;
+  FinishArgs f = base;
+  f.state = states ? states + c : nullptr;
+  if (f.state && f.state->phase == PH_PAUSED) return;
+  f.beta = beta_base + (long long)c * beta_stride;
+  f.res = res + (size_t)c * kResStride;
+  f.p2p = 0;
+  const int cg = c / kTcChains, ci = c % kTcChains;
+  for (int j = threadIdx.x; j <= f.p; j += kBlock) {
+    double s = 0.0;
+    for (int bx = 0; bx < row_ctas; ++bx)
+      s += partials[(((size_t)bx * groups + cg) * (size_t)(P + 1) + j) * kTcChains + ci];
+    s_sums[j] = s;
+  }
+  __syncthreads();
+  finish_eval(f, s_sums, scratch);
+}
+
+}  // namespace lrb

@@ -18,6 +18,7 @@
 #include "data.cuh"
 #include "eval_kernel.cuh"
 #include "eval_mc_kernel.cuh"
+#include "eval_tc_kernel.cuh"
 #include "sampler.cuh"
 
 using namespace lrb;
@@ -170,6 +171,12 @@ struct lrb_handle {
   int run_C = 1, chain_C = 1, graph_C = 1;
   int grid_mc = 0;
   long long graph_kl_per_replay = 0, graph_el_per_replay = 0;
+  // tensor-core many-chain path (fp32 mode, P = 32 or 64)
+  bool tc_ok = false;
+  CUtensorMap xmap{};
+  double* partials_tc = nullptr; size_t partials_tc_cap = 0;
+  float* dbg_eta = nullptr;
+  int tc_min_chains = 32;
 
   long long kernel_launches = 0, eval_launches = 0;
 };
@@ -242,6 +249,33 @@ int configure(lrb_handle* h) {
   drop_graph(h);
   h->chain_live = false;
   h->run_armed = false;
+  // TMA descriptor of X for the tensor-core many-chain kernel
+  h->tc_ok = false;
+  if (h->mode == LRB_MODE_FP32 && (h->P == 32 || h->P == 64) && h->n < (1ll << 31)) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        qres == cudaDriverEntryPointSuccess) {
+      const cuuint64_t dims[2] = {(cuuint64_t)h->P, (cuuint64_t)h->n};
+      const cuuint64_t strides[1] = {(cuuint64_t)h->P * 4};
+      const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
+      const cuuint32_t estr[2] = {1, 1};
+      CUresult r = ((EncodeFn)fn)(&h->xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->X, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      h->tc_ok = (r == CUDA_SUCCESS);
+    }
+    if (h->tc_ok) {
+      cudaError_t e = h->P == 64
+          ? cudaFuncSetAttribute(eval_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<64>::kDynSmem)
+          : cudaFuncSetAttribute(eval_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<32>::kDynSmem);
+      if (e != cudaSuccess) { cudaGetLastError(); h->tc_ok = false; }
+    }
+  }
+  if (const char* env = getenv("LRB_TC_MIN_CHAINS")) h->tc_min_chains = atoi(env);
   return LRB_OK;
 }
 
@@ -339,7 +373,9 @@ int alloc_data(lrb_handle* h, long long n, int p, int mode) {
   h->n = n; h->p = p; h->P = pad_p(p); h->mode = mode;
   const size_t es = mode == LRB_MODE_FP32 ? 4 : 8;
   CK(h, cudaMalloc(&h->X, (size_t)n * h->P * es));
-  CK(h, cudaMalloc(&h->y, (size_t)n));
+  const size_t ybytes = ((size_t)n + 127) / 128 * 128;   // the tensor-core path copies y in 128-byte tiles
+  CK(h, cudaMalloc(&h->y, ybytes));
+  CK(h, cudaMemset(h->y, 0, ybytes));
   return LRB_OK;
 }
 
@@ -412,7 +448,7 @@ extern "C" int lrb_destroy(lrb_handle* h) {
   free_data(h);
   void* bufs[] = {h->d_pscale, h->d_logps, h->partials, h->ticket, h->sums, h->res, h->beta, h->d_init,
                   h->d_scale, h->state, h->seq, h->d_out, h->d_z, h->d_u, h->mailbox,
-                  h->states_mc, h->sums_mc, h->res_mc, h->beta_mc};
+                  h->states_mc, h->sums_mc, h->res_mc, h->beta_mc, h->partials_tc};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -606,10 +642,45 @@ int ensure_chains(lrb_handle* h, int C) {
   return LRB_OK;
 }
 
+bool use_tc(const lrb_handle* h, int C) {
+  return h->tc_ok && h->world == 1 && C >= h->tc_min_chains && (C + kTcChains - 1) / kTcChains <= h->sms;
+}
+
+// Tensor-core many-chain evaluation: one launch of eval_tc_kernel (CTA = 128 chains x a
+// strided set of 128-row tiles) + one finish launch with a CTA per chain.
+int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_stride, int C, SamplerState* states) {
+  const int groups = (C + kTcChains - 1) / kTcChains;
+  const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
+  const int gx = std::max(1, std::min(h->sms / groups, ntiles));
+  const size_t need = (size_t)gx * groups * (h->P + 1) * kTcChains;
+  if (need > h->partials_tc_cap) {
+    if (h->partials_tc) cudaFree(h->partials_tc);
+    h->partials_tc = nullptr; h->partials_tc_cap = 0;
+    CK(h, cudaMalloc(&h->partials_tc, need * sizeof(double)));
+    h->partials_tc_cap = need;
+  }
+  EvalTcArgs a{};
+  a.y = h->y; a.n = h->n; a.ntiles = ntiles;
+  a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
+  a.partials = h->partials_tc; a.states = states; a.dbg_eta = h->dbg_eta;
+  dim3 grid(gx, groups);
+  if (h->P == 64) eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap, a);
+  else eval_tc_kernel<32><<<grid, kTcThreads, TcLayout<32>::kDynSmem, h->stream>>>(h->xmap, a);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  h->eval_launches++;
+  FinishArgs f = finish_args(h, nullptr, nullptr);
+  finish_tc_kernel<<<C, kBlock, 0, h->stream>>>(f, h->partials_tc, gx, groups, h->P, states, beta_base, beta_stride, h->res_mc);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  return LRB_OK;
+}
+
 // Enqueue one fused evaluation of C >= 2 chains: ceil(C/4) passes of the SIMT many-chain
 // kernel (each X batch reused for 4 chains) + one finish launch with a CTA per chain.
 int enqueue_eval_mc(lrb_handle* h, const double* beta_base, long long beta_stride, int C,
                     SamplerState* states) {
+  if (use_tc(h, C)) return enqueue_eval_tc(h, beta_base, beta_stride, C, states);
   constexpr int NC = kMcChains;
   for (int c0 = 0; c0 < C; c0 += NC) {
     EvalMcArgs a{};
@@ -684,6 +755,29 @@ extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
     if (ll) ll[c] = back[1];
     if (glp && want_grad) std::memcpy(glp + (size_t)c * p, back + 3, p * sizeof(double));
   }
+  return LRB_OK;
+}
+
+extern "C" int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float* eta_out) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!h->bound) return fail(h, LRB_E_STATE, "no data bound");
+  if (!h->tc_ok) return fail(h, LRB_E_UNSUPPORTED, "tensor-core path unavailable for this shape/mode");
+  if (!beta || !eta_out || C < 1) return fail(h, LRB_E_BAD_ARG, "bad arguments");
+  if (use_device(h)) return LRB_E_CUDA;
+  int rc = ensure_chains(h, C);
+  if (rc) return rc;
+  const int groups = (C + kTcChains - 1) / kTcChains;
+  const size_t cnt = (size_t)groups * kTcChains * kTcRows;
+  CK(h, cudaMalloc(&h->dbg_eta, cnt * sizeof(float)));
+  CK(h, cudaMemsetAsync(h->dbg_eta, 0, cnt * sizeof(float), h->stream));
+  cudaError_t e = cudaMemcpyAsync(h->beta_mc, beta, (size_t)C * h->p * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) rc = enqueue_eval_tc(h, h->beta_mc, h->p, C, nullptr);
+  if (e == cudaSuccess && rc == LRB_OK) e = cudaMemcpyAsync(eta_out, h->dbg_eta, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == LRB_OK) e = cudaStreamSynchronize(h->stream);
+  cudaFree(h->dbg_eta);
+  h->dbg_eta = nullptr;
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "debug_tc_eta failed: %s", cudaGetErrorString(e));
   return LRB_OK;
 }
 
