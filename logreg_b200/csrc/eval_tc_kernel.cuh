@@ -10,9 +10,11 @@
 // glp fit-np-ul.py:45-48, evaluated for 128 chains x 128 rows per tile.
 //
 // One CTA (384 threads, 1 per SM) owns one group of 128 chains and a strided set of
-// 128-row tiles:
-//   warp 0      TMA producer: X tile (P/32 boxes of 128 rows x 32 floats, 128B swizzle)
-//               + the 128 y bytes, 2-stage mbarrier ring.
+// 64-row tiles:
+//   warp 0      TMA producer: the X tile TWICE (P/32 boxes of 64 rows x 32 floats each):
+//               once with the plain 128-byte swizzle (K-major operand of MMA1) and once
+//               with the 128B/32B-atom swizzle (the only layout tcgen05 accepts for an
+//               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 2-stage ring.
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
 //   warp 2      TMEM allocator (512 columns).
 //   warps 4-7   epilogue: thread = chain (TMEM lane).  tcgen05.ld eta (32 rows at a
@@ -29,8 +31,8 @@
 // and the TMEM (fp32) gradient accumulator is flushed into float64 partial sums in
 // global memory every kFlush tiles (1024 rows).
 //
-// The same smem X tile is the K-major B operand of MMA1 (N = rows, K = p) and the
-// MN-major B operand of MMA2 (N = p, K = rows): no transpose is ever materialised.
+// X is the K-major B operand of MMA1 (N = rows, K = p) and the MN-major B operand of
+// MMA2 (N = p, K = rows): no transpose is ever materialised, TMA delivers both swizzles.
 #pragma once
 #include <cuda.h>
 
@@ -39,21 +41,21 @@
 namespace lrb {
 
 constexpr int kTcThreads = 384;
-constexpr int kTcRows = 128;     // rows per tile (MMA1 N, MMA2 K)
+constexpr int kTcRows = 64;      // rows per tile (MMA1 N, MMA2 K)
 constexpr int kTcChains = 128;   // chains per CTA (MMA M)
-constexpr int kFlush = 8;        // tiles between float64 flushes of the TMEM gradient
+constexpr int kFlush = 16;       // tiles (1024 rows) between float64 flushes of the TMEM gradient
 
 struct EvalTcArgs {
   const uint8_t* y;            // n bytes, allocation padded to a multiple of 128
   long long n;
-  int ntiles;                  // ceil(n / 128)
+  int ntiles;                  // ceil(n / kTcRows)
   const double* beta_base;     // chain c at beta_base + c*beta_stride (doubles)
   long long beta_stride;
   int C;                       // chains
   int p;
   double* partials;            // [gridDim.x][gridDim.y][P+1][128]: col 0 = ll, 1+j = gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
-  float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][128]
+  float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
 };
 
 namespace tc {
@@ -110,10 +112,12 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
       ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (MN-major TF32).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2u) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32.
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -156,30 +160,36 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 
 template <int P>
 struct TcLayout {
-  static constexpr int kBoxes = P / 32;                 // 32-float (128-byte) column boxes per tile
-  static constexpr uint32_t kBoxBytes = 128 * 128;      // 128 rows x 128 bytes
-  static constexpr uint32_t kTileBytes = kBoxes * kBoxBytes;   // X tile == beta tile size
-  static constexpr uint32_t kStageBytes = 2 * kTileBytes;      // X + Xl
+  static constexpr int kBoxes = P / 32;                        // 32-float (128-byte) column boxes per tile
+  static constexpr uint32_t kXBoxBytes = kTcRows * 128;        // X box: 64 rows x 128 bytes
+  static constexpr uint32_t kXTileBytes = kBoxes * kXBoxBytes;
+  static constexpr uint32_t kBBoxBytes = kTcChains * 128;      // beta box: 128 chains x 128 bytes
+  static constexpr uint32_t kBTileBytes = kBoxes * kBBoxBytes;
+  // stage: [Xk | Xlk | Xm | Xlm]  (k = SW128 copy for MMA1, m = SW128/32B-atom copy for MMA2)
+  static constexpr uint32_t kOffXk = 0, kOffXlk = kXTileBytes, kOffXm = 2 * kXTileBytes, kOffXlm = 3 * kXTileBytes;
+  static constexpr uint32_t kStageBytes = 4 * kXTileBytes;
   static constexpr uint32_t kOffBh = 2 * kStageBytes;
-  static constexpr uint32_t kOffBl = kOffBh + kTileBytes;
-  static constexpr uint32_t kOffY = kOffBl + kTileBytes;        // 2 x 128 bytes
+  static constexpr uint32_t kOffBl = kOffBh + kBTileBytes;
+  static constexpr uint32_t kOffY = kOffBl + kBTileBytes;       // 2 x 64 bytes (128-byte slots)
   static constexpr uint32_t kOffBar = kOffY + 256;
   static constexpr uint32_t kNumBar = 14;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBar * 8;
   static constexpr uint32_t kBytes = kOffTmemPtr + 16;
   static constexpr uint32_t kDynSmem = kBytes + 1024;           // manual 1024-byte alignment slack
+  static constexpr uint32_t kTmemCols = 256;                    // eta/R 2 x 64, gradient P <= 64
 };
 
 template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1)
-eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
+eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant__ CUtensorMap xmap_mn,
+               const EvalTcArgs a) {
   using namespace tc;
   using Lay = TcLayout<P>;
   static_assert(P == 32 || P == 64, "tensor-core path supports P = 32 or 64");
   constexpr int KQ = P / 8;            // MMA1 k-chunks (TF32 UMMA_K = 8)
   constexpr int RQ = kTcRows / 8;      // MMA2 k-chunks
-  // TMEM columns: eta/R double buffer [0,256), gradient accumulator [256, 256+P)
-  constexpr uint32_t kColD1 = 0, kColG = 256;
+  // TMEM columns: eta/R double buffer [0, 2*64), gradient accumulator [128, 128+P)
+  constexpr uint32_t kColD1 = 0, kColG = 2 * kTcRows;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -208,7 +218,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + Lay::kOffTmemPtr), "r"(512u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + Lay::kOffTmemPtr), "r"(Lay::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
 
@@ -221,7 +231,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
     const float bh = trunc_tf32((float)b);
     const float bl = (float)(b - (double)bh);
     const int box = k >> 5, kk = k & 31;
-    const uint32_t off = box * Lay::kBoxBytes + c * 128 + ((((uint32_t)kk >> 2) ^ ((uint32_t)c & 7u)) << 4) + (kk & 3) * 4;
+    const uint32_t off = box * Lay::kBBoxBytes + c * 128 + ((((uint32_t)kk >> 2) ^ ((uint32_t)c & 7u)) << 4) + (kk & 3) * 4;
     *reinterpret_cast<float*>(gen + Lay::kOffBh + off) = bh;
     *reinterpret_cast<float*>(gen + Lay::kOffBl + off) = bl;
   }
@@ -238,11 +248,14 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
         const int s = i & 1;
         const int tile = blockIdx.x + i * gridDim.x;
         mbar_wait(bar(X_EMPTY + s), ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(bar(X_FULL + s), Lay::kTileBytes + 128u);
+        mbar_expect_tx(bar(X_FULL + s), 2u * Lay::kXTileBytes + (uint32_t)kTcRows);
         const uint32_t dst = base + s * Lay::kStageBytes;
 #pragma unroll
-        for (int b = 0; b < Lay::kBoxes; ++b) tma_load_2d(dst + b * Lay::kBoxBytes, &xmap, bar(X_FULL + s), 32 * b, tile * kTcRows);
-        bulk_load(base + Lay::kOffY + s * 128, a.y + (long long)tile * kTcRows, 128u, bar(X_FULL + s));
+        for (int b = 0; b < Lay::kBoxes; ++b) {
+          tma_load_2d(dst + Lay::kOffXk + b * Lay::kXBoxBytes, &xmap_k, bar(X_FULL + s), 32 * b, tile * kTcRows);
+          tma_load_2d(dst + Lay::kOffXm + b * Lay::kXBoxBytes, &xmap_mn, bar(X_FULL + s), 32 * b, tile * kTcRows);
+        }
+        bulk_load(base + Lay::kOffY + s * 128, a.y + (long long)tile * kTcRows, (uint32_t)kTcRows, bar(X_FULL + s));
       }
     }
   } else if (warp == 1) {
@@ -260,10 +273,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
         const uint32_t a_t = tmem + kColD1 + s * kTcRows;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {      // Rh.Xh then Rh.Xl
-          const uint32_t xb = xs + half * Lay::kTileBytes;
+          const uint32_t xb = xs + (half == 0 ? Lay::kOffXm : Lay::kOffXlm);
 #pragma unroll
           for (int q = 0; q < RQ; ++q) {
-            const uint64_t bdesc = smem_desc(xb + q * 1024u, Lay::kBoxBytes, 1024u);
+            // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
+            // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
+            const uint64_t bdesc = smem_desc(xb + q * 1024u, Lay::kXBoxBytes, 512u, 1u);
             mma_ts(tmem + kColG, a_t + q * 8, bdesc, idesc2, (first_of_group && half == 0 && q == 0) ? 0u : 1u);
           }
         }
@@ -281,11 +296,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
 #pragma unroll
         for (int term = 0; term < 3; ++term) {
           const uint32_t ab = base + (term == 2 ? Lay::kOffBl : Lay::kOffBh);
-          const uint32_t xb = xs + (term == 1 ? Lay::kTileBytes : 0u);
+          const uint32_t xb = xs + (term == 1 ? Lay::kOffXlk : Lay::kOffXk);
 #pragma unroll
           for (int q = 0; q < KQ; ++q) {
-            const uint32_t koff = (q >> 2) * Lay::kBoxBytes + (q & 3) * 32u;
-            mma_ss(d1, smem_desc(ab + koff, 16u, 1024u), smem_desc(xb + koff, 16u, 1024u), idesc1,
+            const uint32_t koff_a = (q >> 2) * Lay::kBBoxBytes + (q & 3) * 32u;
+            const uint32_t koff_b = (q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u;
+            mma_ss(d1, smem_desc(ab + koff_a, 16u, 1024u), smem_desc(xb + koff_b, 16u, 1024u), idesc1,
                    (term == 0 && q == 0) ? 0u : 1u);
           }
         }
@@ -300,15 +316,18 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
     for (int i = 0; i < ntiles_mine; ++i) {
       const int s = i & 1;
       mbar_wait(bar(X_FULL + s), (i >> 1) & 1);
-      const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes);
-      float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + Lay::kTileBytes);
+#pragma unroll
+      for (int set = 0; set < 2; ++set) {   // both swizzled copies; the offsets are swizzle-agnostic
+        const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXm : Lay::kOffXk));
+        float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXlm : Lay::kOffXlk));
 #pragma unroll 4
-      for (int k = ct; k < (int)(Lay::kTileBytes / 16); k += 128) {
-        const float4 x = src[k];
-        float4 l;
-        l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
-        l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
-        dst[k] = l;
+        for (int k = ct; k < (int)(Lay::kXTileBytes / 16); k += 128) {
+          const float4 x = src[k];
+          float4 l;
+          l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
+          l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
+          dst[k] = l;
+        }
       }
       fence_async_smem();
       mbar_arrive(bar(XL_FULL + s));
@@ -400,7 +419,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap, const EvalTcArgs a) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Lay::kTmemCols));
   }
 }
 

@@ -173,7 +173,7 @@ struct lrb_handle {
   long long graph_kl_per_replay = 0, graph_el_per_replay = 0;
   // tensor-core many-chain path (fp32 mode, P = 32 or 64)
   bool tc_ok = false;
-  CUtensorMap xmap{};
+  CUtensorMap xmap_k{}, xmap_mn{};
   double* partials_tc = nullptr; size_t partials_tc_cap = 0;
   float* dbg_eta = nullptr;
   int tc_min_chains = 32;
@@ -263,10 +263,13 @@ int configure(lrb_handle* h) {
       const cuuint64_t strides[1] = {(cuuint64_t)h->P * 4};
       const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
       const cuuint32_t estr[2] = {1, 1};
-      CUresult r = ((EncodeFn)fn)(&h->xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->X, dims, strides, box, estr,
+      CUresult r = ((EncodeFn)fn)(&h->xmap_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->X, dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      h->tc_ok = (r == CUDA_SUCCESS);
+      CUresult r2 = ((EncodeFn)fn)(&h->xmap_mn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->X, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      h->tc_ok = (r == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
     }
     if (h->tc_ok) {
       cudaError_t e = h->P == 64
@@ -664,8 +667,8 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
   a.partials = h->partials_tc; a.states = states; a.dbg_eta = h->dbg_eta;
   dim3 grid(gx, groups);
-  if (h->P == 64) eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap, a);
-  else eval_tc_kernel<32><<<grid, kTcThreads, TcLayout<32>::kDynSmem, h->stream>>>(h->xmap, a);
+  if (h->P == 64) eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
+  else eval_tc_kernel<32><<<grid, kTcThreads, TcLayout<32>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
   CK(h, cudaGetLastError());
   h->kernel_launches++;
   h->eval_launches++;

@@ -14,10 +14,11 @@ rs = np.random.RandomState(1)
 B = bt + 0.1 * rs.randn(Cn, p)
 X, y = prob.copy_rows(0, min(n, 4096))
 groups = (Cn + 127) // 128
-eta = np.zeros((groups * 128, 128), dtype=np.float32)
+TR = 64
+eta = np.zeros((groups * 128, TR), dtype=np.float32)
 prob._ck(prob._lib.lrb_debug_tc_eta(prob._h, N.as_dp(np.ascontiguousarray(B)), Cn, eta.ctypes.data_as(C.POINTER(C.c_float))))
-ref = (X[:128] @ B.T).T            # [chain][row]
-err = np.abs(eta[:Cn, :min(n, 128)] - ref[:, :min(n, 128)])
+ref = (X[:TR] @ B.T).T            # [chain][row]
+err = np.abs(eta[:Cn, :min(n, TR)] - ref[:, :min(n, TR)])
 print("eta tile0: max abs err", err.max(), "max |eta|", np.abs(ref).max(), "rel", err.max() / np.abs(ref).max(), flush=True)
 if err.max() > 1e-3:
     print("eta sample (dev):", eta[0, :6], "\n           (ref):", ref[0, :6])
@@ -39,3 +40,20 @@ for rep in range(3):
     t0 = time.perf_counter(); prob.eval_many(B); dt = time.perf_counter() - t0
 print(f"all-chain eval C={Cn} n={n} p={p}: {dt*1e3:.3f} ms host-timed -> {dt/Cn*1e6:.2f} us per chain-eval, "
       f"{4*n*p*Cn/dt/1e12:.2f} TFLOP/s (1-pass flops)")
+
+# device-side timing of the all-chain evaluation + a lock-step MALA run
+import torch
+def dev_time(fn, reps=10):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
+sd = 2.2 / np.sqrt(n)
+k = lr.malaKernel(prob.lpost, prob.glp, dt=(0.5 * sd) ** 2, pre=1.0)
+inits = np.tile(bt, (Cn, 1))
+prob.run_chains(k, inits, 1, 5, seed=3)
+t0 = time.perf_counter(); mats, acc = prob.run_chains(k, inits, 1, 50, seed=3); dt = time.perf_counter() - t0
+print(f"lock-step MALA C={Cn}: 50 iters in {dt*1e3:.2f} ms -> {dt/50*1e3:.3f} ms per all-chain step, "
+      f"{Cn*50/dt:.0f} chain-iters/s, accept {acc.mean()/50:.2f}, {4*n*p*Cn*51/dt/1e12:.1f} TFLOP/s")
