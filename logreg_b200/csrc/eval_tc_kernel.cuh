@@ -9,20 +9,22 @@
 // between, per (chain, row).  Reference arithmetic replaced: ll fit-numpy.py:23-24,
 // glp fit-np-ul.py:45-48, evaluated for 128 chains x 128 rows per tile.
 //
-// One CTA (384 threads, 1 per SM) owns one group of 128 chains and a strided set of
+// One CTA (512 threads, 1 per SM) owns one group of 128 chains and a strided set of
 // 64-row tiles:
 //   warp 0      TMA producer: the X tile TWICE (P/32 boxes of 64 rows x 32 floats each):
 //               once with the plain 128-byte swizzle (K-major operand of MMA1) and once
 //               with the 128B/32B-atom swizzle (the only layout tcgen05 accepts for an
-//               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 2-stage ring.
+//               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 3-stage ring.
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
-//   warp 2      TMEM allocator (512 columns).
-//   warps 4-7   epilogue: thread = chain (TMEM lane).  tcgen05.ld eta (32 rows at a
-//               time), link functions, log-likelihood into a per-thread accumulator
-//               (no cross-thread reduction: a thread owns its chain), residual r
-//               rounded to TF32 and written back IN PLACE with tcgen05.st, so MMA2
-//               takes R straight from TMEM as its A operand.
-//   warps 8-11  converters: Xl = X - trunc_tf32(X) into a second smem buffer.
+//   warp 2      TMEM allocator (512 columns: eta/R x2, gradient x2, beta hi, beta lo).
+//   warps 4-11  epilogue: thread = (chain = TMEM lane, 32-row half of the tile).
+//               tcgen05.ld eta, link functions, log-likelihood into a per-thread
+//               accumulator (no cross-thread reduction: a thread owns its chain),
+//               residual r rounded to TF32 and written back IN PLACE with tcgen05.st,
+//               so MMA2 takes R straight from TMEM as its A operand.  beta itself is
+//               the TMEM A operand of MMA1 (written once per launch), which leaves
+//               shared memory for a 3-stage X ring.
+//   warps 12-15 converters: Xl = X - trunc_tf32(X) into the lo buffers; y -> float.
 // Precision (hard part 4): single-pass TF32 cannot meet 1e-5, so
 //   eta = Xh.Bh + Xl.Bh + Xh.Bl   (3 MMAs; the tensor core ignores the 13 low mantissa
 //                                   bits of an fp32 operand, so raw X serves as Xh)
@@ -40,7 +42,7 @@
 
 namespace lrb {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 512;
 constexpr int kTcRows = 64;      // rows per tile (MMA1 N, MMA2 K)
 constexpr int kTcChains = 128;   // chains per CTA (MMA M)
 constexpr int kFlush = 16;       // tiles (1024 rows) between float64 flushes of the TMEM gradient
@@ -53,7 +55,7 @@ struct EvalTcArgs {
   long long beta_stride;
   int C;                       // chains
   int p;
-  double* partials;            // [gridDim.x][gridDim.y][P+1][128]: col 0 = ll, 1+j = gll_j
+  double* partials;            // [gridDim.x][gridDim.y][P+2][128]: rows 0,1 = ll halves, 2+j = gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
   float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
 };
@@ -160,24 +162,54 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 
 template <int P>
 struct TcLayout {
+  static constexpr int kStages = 3;
   static constexpr int kBoxes = P / 32;                        // 32-float (128-byte) column boxes per tile
   static constexpr uint32_t kXBoxBytes = kTcRows * 128;        // X box: 64 rows x 128 bytes
   static constexpr uint32_t kXTileBytes = kBoxes * kXBoxBytes;
-  static constexpr uint32_t kBBoxBytes = kTcChains * 128;      // beta box: 128 chains x 128 bytes
-  static constexpr uint32_t kBTileBytes = kBoxes * kBBoxBytes;
   // stage: [Xk | Xlk | Xm | Xlm]  (k = SW128 copy for MMA1, m = SW128/32B-atom copy for MMA2)
   static constexpr uint32_t kOffXk = 0, kOffXlk = kXTileBytes, kOffXm = 2 * kXTileBytes, kOffXlm = 3 * kXTileBytes;
   static constexpr uint32_t kStageBytes = 4 * kXTileBytes;
-  static constexpr uint32_t kOffBh = 2 * kStageBytes;
-  static constexpr uint32_t kOffBl = kOffBh + kBTileBytes;
-  static constexpr uint32_t kOffY = kOffBl + kBTileBytes;       // 2 x 64 bytes (128-byte slots)
-  static constexpr uint32_t kOffBar = kOffY + 256;
-  static constexpr uint32_t kNumBar = 14;
+  static constexpr uint32_t kOffY = kStages * kStageBytes;      // raw y bytes, one 128-byte slot per stage
+  static constexpr uint32_t kOffYf = kOffY + kStages * 128;     // y as float, 256 bytes per stage
+  static constexpr uint32_t kOffBar = kOffYf + kStages * 256;
+  static constexpr uint32_t kNumBar = 3 * kStages + 8;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBar * 8;
   static constexpr uint32_t kBytes = kOffTmemPtr + 16;
   static constexpr uint32_t kDynSmem = kBytes + 1024;           // manual 1024-byte alignment slack
-  static constexpr uint32_t kTmemCols = 256;                    // eta/R 2 x 64, gradient P <= 64
+  // TMEM columns: eta/R double buffer, gradient double buffer, beta hi / lo (A operand of MMA1)
+  static constexpr uint32_t kColD1 = 0, kColG = 2 * kTcRows, kColBh = kColG + 2 * P, kColBl = kColBh + P;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kColBl + P <= kTmemCols, "TMEM budget");
 };
+
+template <bool TAIL>
+__device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[32], const float4* yf, int valid) {
+  using namespace tc;
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  float acc = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 y4 = yf[k4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k4 * 4 + kk;
+      const float eta = __uint_as_float(v[k]);
+      const float yv = kk == 0 ? y4.x : kk == 1 ? y4.y : kk == 2 ? y4.z : y4.w;
+      const float e = ex2_approx(-fabsf(eta) * LOG2E);
+      const float t = 1.0f + e;
+      const float inv = rcp_approx(t);
+      const float lg = lg2_approx(t);
+      // ll_i = y*eta - max(eta,0) - log1p(exp(-|eta|))
+      float term = fmaf(yv, eta, -fmaxf(eta, 0.0f));
+      term = fmaf(-LN2, lg, term);
+      if (TAIL) term = (k < valid) ? term : 0.0f;
+      acc += term;
+      const float sig = eta >= 0.0f ? inv : e * inv;
+      v[k] = to_tf32_rna(yv - sig);
+    }
+  }
+  return acc;
+}
 
 template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -185,11 +217,10 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
                const EvalTcArgs a) {
   using namespace tc;
   using Lay = TcLayout<P>;
-  static_assert(P == 32 || P == 64, "tensor-core path supports P = 32 or 64");
+  static_assert(P == 64, "tensor-core path: P = 64");
+  constexpr int NS = Lay::kStages;
   constexpr int KQ = P / 8;            // MMA1 k-chunks (TF32 UMMA_K = 8)
   constexpr int RQ = kTcRows / 8;      // MMA2 k-chunks
-  // TMEM columns: eta/R double buffer [0, 2*64), gradient accumulator [128, 128+P)
-  constexpr uint32_t kColD1 = 0, kColG = 2 * kTcRows;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -202,52 +233,68 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   const int ntiles_mine = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   auto bar = [&](int i) { return base + Lay::kOffBar + 8u * i; };
-  // barrier indices
-  constexpr int X_FULL = 0, XL_FULL = 2, X_EMPTY = 4, D1_FULL = 6, R_FULL = 8, G_FULL = 10, G_FREE = 11;
+  constexpr int X_FULL = 0, XL_FULL = NS, X_EMPTY = 2 * NS, D1_FULL = 3 * NS, R_FULL = 3 * NS + 2,
+                G_FULL = 3 * NS + 4, G_FREE = 3 * NS + 6;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(bar(X_FULL + s), 1);
       mbar_init(bar(XL_FULL + s), 128);
       mbar_init(bar(X_EMPTY + s), 1);
-      mbar_init(bar(D1_FULL + s), 1);
-      mbar_init(bar(R_FULL + s), 128);
     }
-    mbar_init(bar(G_FULL), 1);
-    mbar_init(bar(G_FREE), 128);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(D1_FULL + b), 1);
+      mbar_init(bar(R_FULL + b), 256);
+      mbar_init(bar(G_FULL + b), 1);
+      mbar_init(bar(G_FREE + b), 256);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + Lay::kOffTmemPtr), "r"(Lay::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-
-  // beta tile of this chain group -> smem (K-major, 128-byte swizzle), hi and lo parts
-  for (int idx = tid; idx < kTcChains * P; idx += kTcThreads) {
-    const int c = idx / P, k = idx % P;
-    const int chain = cg * kTcChains + c;
-    double b = 0.0;
-    if (chain < a.C && k < a.p) b = a.beta_base[(long long)chain * a.beta_stride + k];
-    const float bh = trunc_tf32((float)b);
-    const float bl = (float)(b - (double)bh);
-    const int box = k >> 5, kk = k & 31;
-    const uint32_t off = box * Lay::kBBoxBytes + c * 128 + ((((uint32_t)kk >> 2) ^ ((uint32_t)c & 7u)) << 4) + (kk & 3) * 4;
-    *reinterpret_cast<float*>(gen + Lay::kOffBh + off) = bh;
-    *reinterpret_cast<float*>(gen + Lay::kOffBl + off) = bl;
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + Lay::kOffTmemPtr);
 
+  const bool is_epi = warp >= 4 && warp < 12;
+  const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+  const int half = (warp - 4) >> 2;                 // epilogue: which 32 rows of a tile / which 32 G columns
+  const int ci = quarter * 32 + lane;               // chain within the group == TMEM lane
+  const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
+
+  // beta of this chain group -> TMEM (A operand of MMA1): half 0 writes the TF32 hi part,
+  // half 1 the remainder beta - hi
+  if (is_epi) {
+    const int chain = cg * kTcChains + ci;
+    const double* bsrc = a.beta_base + (long long)chain * a.beta_stride;
+#pragma unroll 1
+    for (int ch = 0; ch < P / 32; ++ch) {
+      uint32_t v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int col = ch * 32 + k;
+        const double b = (chain < a.C && col < a.p) ? bsrc[col] : 0.0;
+        const float bh = trunc_tf32((float)b);
+        v[k] = __float_as_uint(half == 0 ? bh : (float)(b - (double)bh));
+      }
+      tmem_st32(tmem + lane_addr + (half == 0 ? Lay::kColBh : Lay::kColBl) + ch * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
   if (warp == 0) {
     // ===================== TMA producer
     if (lane == 0) {
       for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i & 1;
+        const int s = i % NS;
         const int tile = blockIdx.x + i * gridDim.x;
-        mbar_wait(bar(X_EMPTY + s), ((i >> 1) & 1) ^ 1);
+        mbar_wait(bar(X_EMPTY + s), ((i / NS) & 1) ^ 1);
         mbar_expect_tx(bar(X_FULL + s), 2u * Lay::kXTileBytes + (uint32_t)kTcRows);
         const uint32_t dst = base + s * Lay::kStageBytes;
 #pragma unroll
@@ -261,63 +308,64 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (K-major), B = X rows (K-major)
+      constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (TMEM), B = X rows (K-major)
       constexpr uint32_t idesc2 = instr_desc(kTcChains, P, 0, 1);         // A = R (TMEM), B = X (MN-major)
       auto issue_mma2 = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(bar(R_FULL + s), (j >> 1) & 1);
+        const int s = j % NS, b = j & 1, g = j / kFlush, gb = g & 1;
+        mbar_wait(bar(R_FULL + b), (j >> 1) & 1);
         tc_fence_after();
         const bool first_of_group = (j % kFlush) == 0;
-        if (first_of_group && j > 0) mbar_wait(bar(G_FREE), ((j / kFlush) - 1) & 1);
+        if (first_of_group && g >= 2) { mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1); tc_fence_after(); }
         const uint32_t xs = base + s * Lay::kStageBytes;
-        const uint32_t a_t = tmem + kColD1 + s * kTcRows;
+        const uint32_t a_t = tmem + Lay::kColD1 + b * kTcRows;
+        const uint32_t d_t = tmem + Lay::kColG + gb * P;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {      // Rh.Xh then Rh.Xl
-          const uint32_t xb = xs + (half == 0 ? Lay::kOffXm : Lay::kOffXlm);
+        for (int hl = 0; hl < 2; ++hl) {      // Rh.Xh then Rh.Xl
+          const uint32_t xb = xs + (hl == 0 ? Lay::kOffXm : Lay::kOffXlm);
 #pragma unroll
           for (int q = 0; q < RQ; ++q) {
             // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
             // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
             const uint64_t bdesc = smem_desc(xb + q * 1024u, Lay::kXBoxBytes, 512u, 1u);
-            mma_ts(tmem + kColG, a_t + q * 8, bdesc, idesc2, (first_of_group && half == 0 && q == 0) ? 0u : 1u);
+            mma_ts(d_t, a_t + q * 8, bdesc, idesc2, (first_of_group && hl == 0 && q == 0) ? 0u : 1u);
           }
         }
-        tc_commit(bar(X_EMPTY + s));                 // stage s (X, Xl, R) is free again
-        if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL));
+        tc_commit(bar(X_EMPTY + s));                 // stage s and eta/R buffer b are free again
+        if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL + gb));
       };
       for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i & 1;
-        mbar_wait(bar(X_FULL + s), (i >> 1) & 1);
-        mbar_wait(bar(XL_FULL + s), (i >> 1) & 1);
+        const int s = i % NS, b = i & 1;
+        mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+        mbar_wait(bar(XL_FULL + s), (i / NS) & 1);
         tc_fence_after();
         const uint32_t xs = base + s * Lay::kStageBytes;
-        const uint32_t d1 = tmem + kColD1 + s * kTcRows;
+        const uint32_t d1 = tmem + Lay::kColD1 + b * kTcRows;
         // eta' = Bh.Xh' + Bh.Xl' + Bl.Xh'
 #pragma unroll
         for (int term = 0; term < 3; ++term) {
-          const uint32_t ab = base + (term == 2 ? Lay::kOffBl : Lay::kOffBh);
+          const uint32_t at = tmem + (term == 2 ? Lay::kColBl : Lay::kColBh);
           const uint32_t xb = xs + (term == 1 ? Lay::kOffXlk : Lay::kOffXk);
 #pragma unroll
           for (int q = 0; q < KQ; ++q) {
-            const uint32_t koff_a = (q >> 2) * Lay::kBBoxBytes + (q & 3) * 32u;
-            const uint32_t koff_b = (q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u;
-            mma_ss(d1, smem_desc(ab + koff_a, 16u, 1024u), smem_desc(xb + koff_b, 16u, 1024u), idesc1,
-                   (term == 0 && q == 0) ? 0u : 1u);
+            const uint32_t koff = (q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u;
+            mma_ts(d1, at + q * 8, smem_desc(xb + koff, 16u, 1024u), idesc1, (term == 0 && q == 0) ? 0u : 1u);
           }
         }
-        tc_commit(bar(D1_FULL + s));
+        tc_commit(bar(D1_FULL + b));
         if (i > 0) issue_mma2(i - 1);
       }
       if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
     }
-  } else if (warp >= 8) {
-    // ===================== converters: Xl = X - trunc_tf32(X), same (swizzled) offsets
-    const int ct = tid - 256;
+  } else if (warp >= 12) {
+    // ===================== converters: Xl = X - trunc_tf32(X) (same swizzled offsets), y -> float
+    const int ct = tid - 384;
     for (int i = 0; i < ntiles_mine; ++i) {
-      const int s = i & 1;
-      mbar_wait(bar(X_FULL + s), (i >> 1) & 1);
+      const int s = i % NS;
+      mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+      if (ct < kTcRows)
+        reinterpret_cast<float*>(gen + Lay::kOffYf + s * 256)[ct] = (float)(gen + Lay::kOffY + s * 128)[ct];
 #pragma unroll
-      for (int set = 0; set < 2; ++set) {   // both swizzled copies; the offsets are swizzle-agnostic
+      for (int set = 0; set < 2; ++set) {
         const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXm : Lay::kOffXk));
         float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXlm : Lay::kOffXlk));
 #pragma unroll 4
@@ -332,86 +380,54 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       fence_async_smem();
       mbar_arrive(bar(XL_FULL + s));
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: thread = chain
-    const int ci = (warp & 3) * 32 + lane;                 // chain within the group == TMEM lane
-    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+  } else if (is_epi) {
+    // ===================== epilogue: thread = (chain, 32-row half of the tile)
     double ll_acc = 0.0;
-    double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)(P + 1) * kTcChains;
-    bool first_flush = true;
-    int flushes = 0;
-    const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-    for (int i = 0; i < ntiles_mine; ++i) {
-      const int s = i & 1;
-      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows;
-      const bool full = row0 + kTcRows <= a.n;
-      mbar_wait(bar(D1_FULL + s), (i >> 1) & 1);
+    double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)(P + 2) * kTcChains;
+    // flush gradient group g (TMEM fp32 accumulator) into the float64 partial sums;
+    // this thread owns 32 of the P columns of its chain
+    auto flush = [&](int g) {
+      const int gb = g & 1;
+      mbar_wait(bar(G_FULL + gb), (g >> 1) & 1);
       tc_fence_after();
-      const uint32_t* ys = reinterpret_cast<const uint32_t*>(gen + Lay::kOffY + s * 128);
-      float ll_tile = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < kTcRows / 32; ++ch) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem + lane_addr + kColD1 + s * kTcRows + ch * 32;
-        tmem_ld32(taddr, v);
-        if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
+      uint32_t gv[32];
+      tmem_ld32(tmem + lane_addr + Lay::kColG + gb * P + half * 32, gv);
+      tc_fence_before();
+      mbar_arrive(bar(G_FREE + gb));
 #pragma unroll
-          for (int k = 0; k < 32; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + ch * 32 + k] = __uint_as_float(v[k]);
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const uint32_t y4 = ys[ch * 8 + k4];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int k = k4 * 4 + kk;
-            const float eta = __uint_as_float(v[k]);
-            const bool y1 = ((y4 >> (8 * kk)) & 0xFFu) != 0u;
-            const float ae = fabsf(eta);
-            const float e = ex2_approx(-ae * LOG2E);
-            const float t = 1.0f + e;
-            const float inv = rcp_approx(t);
-            const float l1p = lg2_approx(t) * LN2;
-            const bool pos = eta >= 0.0f;
-            const float sm = e * inv;
-            const float pr = pos ? inv : sm;               // sigmoid(eta)
-            const float r = y1 ? (pos ? sm : inv) : -pr;   // y - sigmoid(eta), cancellation-free
-            const float z = y1 ? eta : -eta;
-            float lt = fminf(z, 0.0f) - l1p;
-            if (!full && row0 + ch * 32 + k >= a.n) lt = 0.0f;
-            ll_tile += lt;
-            v[k] = to_tf32_rna(r);
-          }
-        }
-        tmem_st32(taddr, v);
+      for (int k = 0; k < 32; ++k) {
+        double* dst = part + (size_t)(2 + half * 32 + k) * kTcChains + ci;
+        const double add = (double)__uint_as_float(gv[k]);
+        *dst = (g == 0) ? add : (*dst + add);
       }
+    };
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i % NS, b = i & 1;
+      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + half * 32;
+      mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
+      tc_fence_after();
+      const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + half * 128);
+      uint32_t v[32];
+      const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + half * 32;
+      tmem_ld32(taddr, v);
+      if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + half * 32 + k] = __uint_as_float(v[k]);
+      }
+      float ll_tile;
+      if (row0 + 32 <= a.n) ll_tile = tc_link_chunk<false>(v, yf, 32);
+      else ll_tile = tc_link_chunk<true>(v, yf, (int)max(0ll, a.n - row0));
+      tmem_st32(taddr, v);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar(R_FULL + s));
+      mbar_arrive(bar(R_FULL + b));
       ll_acc += (double)ll_tile;
-
-      if ((i % kFlush) == kFlush - 1 || i == ntiles_mine - 1) {
-        // flush the fp32 TMEM gradient accumulator into float64 partial sums
-        mbar_wait(bar(G_FULL), flushes & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int ch = 0; ch < P / 32; ++ch) {
-          uint32_t g[32];
-          tmem_ld32(tmem + lane_addr + kColG + ch * 32, g);
-          if (ch == P / 32 - 1) { tc_fence_before(); mbar_arrive(bar(G_FREE)); }
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            double* dst = part + (size_t)(1 + ch * 32 + k) * kTcChains + ci;
-            const double add = (double)__uint_as_float(g[k]);
-            *dst = first_flush ? add : (*dst + add);
-          }
-        }
-        first_flush = false;
-        ++flushes;
-      }
+      if ((i % kFlush) == 0 && i > 0) flush(i / kFlush - 1);   // deferred: the group's MMA2s are long done
     }
-    part[ci] = ll_acc;
+    if (ntiles_mine > 0) flush((ntiles_mine - 1) / kFlush);
+    part[(size_t)half * kTcChains + ci] = ll_acc;
     if (ntiles_mine == 0) {
-      for (int j = 0; j < P; ++j) part[(size_t)(1 + j) * kTcChains + ci] = 0.0;
+      for (int k = 0; k < 32; ++k) part[(size_t)(2 + half * 32 + k) * kTcChains + ci] = 0.0;
     }
   }
 
@@ -425,6 +441,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
 
 // One CTA per chain: sum the per-CTA float64 partials over row CTAs in a fixed order,
 // then the common finish (prior, result, sampler update).
+// partials: [row_ctas][groups][P+2][128]; rows 0,1 = the two log-likelihood halves, 2+j = gll_j
 __global__ void finish_tc_kernel(FinishArgs base, const double* partials, int row_ctas, int groups, int P,
                                  SamplerState* states, const double* beta_base, long long beta_stride,
                                  double* res) {
@@ -440,8 +457,10 @@ __global__ void finish_tc_kernel(FinishArgs base, const double* partials, int ro
   const int cg = c / kTcChains, ci = c % kTcChains;
   for (int j = threadIdx.x; j <= f.p; j += kBlock) {
     double s = 0.0;
-    for (int bx = 0; bx < row_ctas; ++bx)
-      s += partials[(((size_t)bx * groups + cg) * (size_t)(P + 1) + j) * kTcChains + ci];
+    for (int bx = 0; bx < row_ctas; ++bx) {
+      const double* pb = partials + ((size_t)bx * groups + cg) * (size_t)(P + 2) * kTcChains;
+      s += (j == 0) ? (pb[ci] + pb[kTcChains + ci]) : pb[(size_t)(1 + j) * kTcChains + ci];
+    }
     s_sums[j] = s;
   }
   __syncthreads();

@@ -251,7 +251,7 @@ int configure(lrb_handle* h) {
   h->run_armed = false;
   // TMA descriptor of X for the tensor-core many-chain kernel
   h->tc_ok = false;
-  if (h->mode == LRB_MODE_FP32 && (h->P == 32 || h->P == 64) && h->n < (1ll << 31)) {
+  if (h->mode == LRB_MODE_FP32 && h->P == 64 && h->n < (1ll << 31)) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -272,9 +272,8 @@ int configure(lrb_handle* h) {
       h->tc_ok = (r == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
     }
     if (h->tc_ok) {
-      cudaError_t e = h->P == 64
-          ? cudaFuncSetAttribute(eval_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<64>::kDynSmem)
-          : cudaFuncSetAttribute(eval_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<32>::kDynSmem);
+      cudaError_t e = cudaFuncSetAttribute(eval_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TcLayout<64>::kDynSmem);
       if (e != cudaSuccess) { cudaGetLastError(); h->tc_ok = false; }
     }
   }
@@ -655,7 +654,7 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   const int groups = (C + kTcChains - 1) / kTcChains;
   const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
   const int gx = std::max(1, std::min(h->sms / groups, ntiles));
-  const size_t need = (size_t)gx * groups * (h->P + 1) * kTcChains;
+  const size_t need = (size_t)gx * groups * (h->P + 2) * kTcChains;
   if (need > h->partials_tc_cap) {
     if (h->partials_tc) cudaFree(h->partials_tc);
     h->partials_tc = nullptr; h->partials_tc_cap = 0;
@@ -667,8 +666,7 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
   a.partials = h->partials_tc; a.states = states; a.dbg_eta = h->dbg_eta;
   dim3 grid(gx, groups);
-  if (h->P == 64) eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
-  else eval_tc_kernel<32><<<grid, kTcThreads, TcLayout<32>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
+  eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
   CK(h, cudaGetLastError());
   h->kernel_launches++;
   h->eval_launches++;

@@ -329,3 +329,64 @@ def test_lockstep_chains_replay_reference(lr, pima):
                                  Z=np.tile(Z, (C, 1, 1)), U=np.tile(U, (C, 1)))
     for c in range(C):
         np.testing.assert_allclose(mats[c], ref, rtol=1e-7, atol=1e-7)
+
+
+# ---------------------------------------------------------------- tensor-core (tcgen05) many-chain path
+def _tc_problem(lr, n, p=64, seed=42):
+    prob = lr.Problem()
+    bt = prob.gen_synthetic(n, p, mode="fp32", seed=seed)
+    return prob, bt
+
+
+@pytest.mark.parametrize("n,C", [(64, 32), (100, 40), (8192, 128), (100_003, 130), (300_000, 512)])
+def test_tensor_core_many_chain_eval_against_oracle(lr, n, C):
+    """C >= 32 chains in FP32 mode with p = 64 run on the tcgen05 kernel (3xTF32): compare with
+    the oracle on the same rows -- FP32-mode tolerance 1e-5 (lpost relative to itself, glp
+    relative to the un-cancelled gradient magnitude). Covers ragged n (tail tile, TMA
+    zero-fill) and chain counts that are not a multiple of 128."""
+    from tests.helpers import ungrad_scale
+    prob, bt = _tc_problem(lr, n)
+    X, y = prob.copy_rows(0, n)
+    tgt = O.Target(X, y, prob.pscale)
+    rs = np.random.RandomState(7)
+    B = bt + 0.3 * rs.randn(C, 64) / 8
+    B[0] = 0.0
+    lp, l, g = prob.eval_many(B)
+    for c in list(range(0, C, max(1, C // 6))) + [C - 1]:
+        with np.errstate(over="ignore"):
+            ref_lp, ref_g = O.stable_ll(X, y, B[c]) + tgt.lprior(B[c]), tgt.glp(B[c])
+        assert abs(lp[c] - ref_lp) <= 1e-5 * max(1.0, abs(ref_lp)), (c, lp[c], ref_lp)
+        assert np.max(np.abs(g[c] - ref_g)) <= 1e-5 * ungrad_scale(X, y, B[c], prob.pscale), c
+    if n >= 64:
+        assert l[0] == pytest.approx(-n * np.log(2.0), rel=1e-6)
+
+
+def test_tensor_core_eta_tile(lr):
+    """The contraction itself: eta of the first 64-row tile as the tensor cores produce it."""
+    import ctypes as C
+    from logreg_b200 import _native as N
+    prob, bt = _tc_problem(lr, 4096)
+    X, y = prob.copy_rows(0, 64)
+    B = bt + 0.1 * np.random.RandomState(1).randn(256, 64)
+    eta = np.zeros((256, 64), dtype=np.float32)
+    prob._ck(prob._lib.lrb_debug_tc_eta(prob._h, N.as_dp(np.ascontiguousarray(B)), 256,
+                                        eta.ctypes.data_as(C.POINTER(C.c_float))))
+    ref = (X @ B.T).T
+    assert np.max(np.abs(eta - ref)) <= 2e-6 * np.max(np.abs(X)) * np.max(np.abs(B)) * 64
+
+
+def test_tensor_core_lockstep_mala_matches_simt_path(lr):
+    """512 MALA chains for 30 steps on the tcgen05 path vs the same chains on the single-chain
+    float32 kernel: same Philox keys; float32-level agreement until a near-tie decision."""
+    prob, bt = _tc_problem(lr, 200_000)
+    sd = 2.2 / np.sqrt(200_000)
+    k = lr.malaKernel(prob.lpost, prob.glp, dt=(0.5 * sd) ** 2, pre=1.0)
+    C = 512
+    inits = bt + 0.5 * sd * np.random.RandomState(3).randn(C, 64)
+    mats, accs = prob.run_chains(k, inits, 1, 30, seed=5)
+    assert 0.5 < accs.mean() / 30 <= 1.0
+    for c in (0, 17, 255, 511):
+        m1, a1 = prob.run(k, inits[c], 1, 30, seed=(5 + c * 0x9E3779B97F4A7C15) % 2 ** 64)
+        same = np.all(np.abs(mats[c] - m1) < 5e-3 * sd, axis=1)
+        first_bad = len(same) if same.all() else int(np.argmin(same))
+        assert first_bad >= 10, (c, first_bad)
