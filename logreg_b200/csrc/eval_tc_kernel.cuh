@@ -28,8 +28,7 @@
 // Precision (hard part 4): single-pass TF32 cannot meet 1e-5, so
 //   eta = Xh.Bh + Xl.Bh + Xh.Bl   (3 MMAs; the tensor core ignores the 13 low mantissa
 //                                   bits of an fp32 operand, so raw X serves as Xh)
-//   G   = Rh.Xh + Rh.Xl           (R rounded to nearest TF32: unbiased, 2^-12 relative,
-//                                   averaged over >= thousands of rows)
+//   G   = Rh.Xh + Rh.Xl + Rl.Xh   (the residual is split the same way by the epilogue)
 // and the TMEM (fp32) gradient accumulator is flushed into float64 partial sums in
 // global memory every kFlush tiles (1024 rows).
 //
@@ -176,14 +175,19 @@ struct TcLayout {
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBar * 8;
   static constexpr uint32_t kBytes = kOffTmemPtr + 16;
   static constexpr uint32_t kDynSmem = kBytes + 1024;           // manual 1024-byte alignment slack
-  // TMEM columns: eta/R double buffer, gradient double buffer, beta hi / lo (A operand of MMA1)
-  static constexpr uint32_t kColD1 = 0, kColG = 2 * kTcRows, kColBh = kColG + 2 * P, kColBl = kColBh + P;
+  // TMEM columns: eta / R-hi double buffer, R-lo double buffer, gradient double buffer,
+  // beta hi / lo (A operand of MMA1)
+  static constexpr uint32_t kColD1 = 0, kColRl = 2 * kTcRows, kColG = 4 * kTcRows, kColBh = kColG + 2 * P,
+                            kColBl = kColBh + P;
   static constexpr uint32_t kTmemCols = 512;
   static_assert(kColBl + P <= kTmemCols, "TMEM budget");
 };
 
+// Link functions for 32 rows of one chain: v holds eta on entry, the TF32 hi part of the
+// residual r = y - sigmoid(eta) on exit; w receives the remainder r - hi. Returns the
+// log-likelihood contribution sum_i [y*eta - max(eta,0) - log1p(exp(-|eta|))].
 template <bool TAIL>
-__device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[32], const float4* yf, int valid) {
+__device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[32], uint32_t (&w)[32], const float4* yf, int valid) {
   using namespace tc;
   const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   float acc = 0.f;
@@ -197,15 +201,17 @@ __device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[32], const float4* 
       const float yv = kk == 0 ? y4.x : kk == 1 ? y4.y : kk == 2 ? y4.z : y4.w;
       const float e = ex2_approx(-fabsf(eta) * LOG2E);
       const float t = 1.0f + e;
-      const float inv = rcp_approx(t);
+      const float inv = rcp_approx(t);                   // sigmoid(|eta|)
       const float lg = lg2_approx(t);
-      // ll_i = y*eta - max(eta,0) - log1p(exp(-|eta|))
       float term = fmaf(yv, eta, -fmaxf(eta, 0.0f));
       term = fmaf(-LN2, lg, term);
       if (TAIL) term = (k < valid) ? term : 0.0f;
       acc += term;
-      const float sig = eta >= 0.0f ? inv : e * inv;
-      v[k] = to_tf32_rna(yv - sig);
+      const float sig = eta >= 0.0f ? inv : 1.0f - inv;  // e/(1+e) = 1 - 1/(1+e)
+      const float r = yv - sig;
+      const float rh = trunc_tf32(r);
+      v[k] = __float_as_uint(rh);
+      w[k] = __float_as_uint(r - rh);
     }
   }
   return acc;
@@ -317,11 +323,11 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         const bool first_of_group = (j % kFlush) == 0;
         if (first_of_group && g >= 2) { mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1); tc_fence_after(); }
         const uint32_t xs = base + s * Lay::kStageBytes;
-        const uint32_t a_t = tmem + Lay::kColD1 + b * kTcRows;
         const uint32_t d_t = tmem + Lay::kColG + gb * P;
 #pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {      // Rh.Xh then Rh.Xl
-          const uint32_t xb = xs + (hl == 0 ? Lay::kOffXm : Lay::kOffXlm);
+        for (int hl = 0; hl < 3; ++hl) {      // Rh.Xh, Rh.Xl, Rl.Xh
+          const uint32_t a_t = tmem + (hl == 2 ? Lay::kColRl : Lay::kColD1) + b * kTcRows;
+          const uint32_t xb = xs + (hl == 1 ? Lay::kOffXlm : Lay::kOffXm);
 #pragma unroll
           for (int q = 0; q < RQ; ++q) {
             // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
@@ -415,9 +421,11 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         for (int k = 0; k < 32; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + half * 32 + k] = __uint_as_float(v[k]);
       }
       float ll_tile;
-      if (row0 + 32 <= a.n) ll_tile = tc_link_chunk<false>(v, yf, 32);
-      else ll_tile = tc_link_chunk<true>(v, yf, (int)max(0ll, a.n - row0));
+      uint32_t w[32];
+      if (row0 + 32 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 32);
+      else ll_tile = tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
       tmem_st32(taddr, v);
+      tmem_st32(tmem + lane_addr + Lay::kColRl + b * kTcRows + half * 32, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(R_FULL + b));

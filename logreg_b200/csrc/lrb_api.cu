@@ -648,6 +648,21 @@ bool use_tc(const lrb_handle* h, int C) {
   return h->tc_ok && h->world == 1 && C >= h->tc_min_chains && (C + kTcChains - 1) / kTcChains <= h->sms;
 }
 
+// Scratch for the tensor-core path; must be reserved outside stream capture.
+int reserve_tc(lrb_handle* h, int C) {
+  if (!use_tc(h, C)) return LRB_OK;
+  const int groups = (C + kTcChains - 1) / kTcChains;
+  const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
+  const int gx = std::max(1, std::min(h->sms / groups, ntiles));
+  const size_t need = (size_t)gx * groups * (h->P + 2) * kTcChains;
+  if (need <= h->partials_tc_cap) return LRB_OK;
+  if (h->partials_tc) cudaFree(h->partials_tc);
+  h->partials_tc = nullptr; h->partials_tc_cap = 0;
+  CK(h, cudaMalloc(&h->partials_tc, need * sizeof(double)));
+  h->partials_tc_cap = need;
+  return LRB_OK;
+}
+
 // Tensor-core many-chain evaluation: one launch of eval_tc_kernel (CTA = 128 chains x a
 // strided set of 128-row tiles) + one finish launch with a CTA per chain.
 int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_stride, int C, SamplerState* states) {
@@ -655,12 +670,7 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
   const int gx = std::max(1, std::min(h->sms / groups, ntiles));
   const size_t need = (size_t)gx * groups * (h->P + 2) * kTcChains;
-  if (need > h->partials_tc_cap) {
-    if (h->partials_tc) cudaFree(h->partials_tc);
-    h->partials_tc = nullptr; h->partials_tc_cap = 0;
-    CK(h, cudaMalloc(&h->partials_tc, need * sizeof(double)));
-    h->partials_tc_cap = need;
-  }
+  if (need > h->partials_tc_cap) return fail(h, LRB_E_STATE, "tensor-core scratch not reserved (internal error)");
   EvalTcArgs a{};
   a.y = h->y; a.n = h->n; a.ntiles = ntiles;
   a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
@@ -731,6 +741,7 @@ extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
     // many-chain path: X is streamed once per 4 chains
     int rc = ensure_chains(h, C);
     if (rc) return rc;
+    if ((rc = reserve_tc(h, C))) return rc;
     CK(h, cudaMemcpyAsync(h->beta_mc, beta, (size_t)C * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if ((rc = enqueue_eval_mc(h, h->beta_mc, p, C, nullptr))) return rc;
     std::vector<double> back((size_t)C * kResStride);
@@ -767,6 +778,8 @@ extern "C" int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float*
   if (use_device(h)) return LRB_E_CUDA;
   int rc = ensure_chains(h, C);
   if (rc) return rc;
+  if ((rc = reserve_tc(h, C))) return rc;
+  if (!use_tc(h, C)) return fail(h, LRB_E_UNSUPPORTED, "C below the tensor-core threshold");
   const int groups = (C + kTcChains - 1) / kTcChains;
   const size_t cnt = (size_t)groups * kTcChains * kTcRows;
   CK(h, cudaMalloc(&h->dbg_eta, cnt * sizeof(float)));
@@ -872,6 +885,7 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   const long long steps = thin * iters;
   int rc;
   if (C > 1 && (rc = ensure_chains(h, C))) return rc;
+  if (C > 1 && (rc = reserve_tc(h, C))) return rc;
   if ((rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)C * iters * p)))) return rc;
   const double *dz = nullptr, *du = nullptr;
   if (params->rng == LRB_RNG_REPLAY && steps > 0) {
