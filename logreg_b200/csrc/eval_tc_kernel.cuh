@@ -9,7 +9,7 @@
 // between, per (chain, row).  Reference arithmetic replaced: ll fit-numpy.py:23-24,
 // glp fit-np-ul.py:45-48, evaluated for 128 chains x 128 rows per tile.
 //
-// One CTA (512 threads, 1 per SM) owns one group of 128 chains and a strided set of
+// One CTA (768 threads, 1 per SM) owns one group of 128 chains and a strided set of
 // 64-row tiles:
 //   warp 0      TMA producer: the X tile TWICE (P/32 boxes of 64 rows x 32 floats each):
 //               once with the plain 128-byte swizzle (K-major operand of MMA1) and once
@@ -17,14 +17,15 @@
 //               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 3-stage ring.
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
 //   warp 2      TMEM allocator (512 columns: eta/R x2, gradient x2, beta hi, beta lo).
-//   warps 4-11  epilogue: thread = (chain = TMEM lane, 32-row half of the tile).
+//   warps 4-19  epilogue: thread = (chain = TMEM lane, 16-row slice of the tile); four
+//               warps per scheduler keep the MUFU pipe (3 ops per element) busy.
 //               tcgen05.ld eta, link functions, log-likelihood into a per-thread
 //               accumulator (no cross-thread reduction: a thread owns its chain),
 //               residual r rounded to TF32 and written back IN PLACE with tcgen05.st,
 //               so MMA2 takes R straight from TMEM as its A operand.  beta itself is
 //               the TMEM A operand of MMA1 (written once per launch), which leaves
 //               shared memory for a 3-stage X ring.
-//   warps 12-15 converters: Xl = X - trunc_tf32(X) into the lo buffers; y -> float.
+//   warps 20-23 converters: Xl = X - trunc_tf32(X) into the lo buffers; y -> float.
 // Precision (hard part 4): single-pass TF32 cannot meet 1e-5, so
 //   eta = Xh.Bh + Xl.Bh + Xh.Bl   (3 MMAs; the tensor core ignores the 13 low mantissa
 //                                   bits of an fp32 operand, so raw X serves as Xh)
@@ -41,7 +42,8 @@
 
 namespace lrb {
 
-constexpr int kTcThreads = 512;
+constexpr int kTcThreads = 768;   // 4 control warps + 16 epilogue warps + 4 converter warps
+constexpr int kTcSub = 4;         // epilogue warps per TMEM lane quarter (16 rows of a tile each)
 constexpr int kTcRows = 64;      // rows per tile (MMA1 N, MMA2 K)
 constexpr int kTcChains = 128;   // chains per CTA (MMA M)
 constexpr int kFlush = 16;       // tiles (1024 rows) between float64 flushes of the TMEM gradient
@@ -54,7 +56,7 @@ struct EvalTcArgs {
   long long beta_stride;
   int C;                       // chains
   int p;
-  double* partials;            // [gridDim.x][gridDim.y][P+2][128]: rows 0,1 = ll halves, 2+j = gll_j
+  double* partials;            // [gridDim.x][gridDim.y][P+kTcSub][128]: ll slices, then gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
   float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
 };
@@ -90,6 +92,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// true in exactly one lane of a converged warp (the others fall through)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -149,6 +157,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -183,16 +208,16 @@ struct TcLayout {
   static_assert(kColBl + P <= kTmemCols, "TMEM budget");
 };
 
-// Link functions for 32 rows of one chain: v holds eta on entry, the TF32 hi part of the
+// Link functions for 16 rows of one chain: v holds eta on entry, the TF32 hi part of the
 // residual r = y - sigmoid(eta) on exit; w receives the remainder r - hi. Returns the
 // log-likelihood contribution sum_i [y*eta - max(eta,0) - log1p(exp(-|eta|))].
 template <bool TAIL>
-__device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[32], uint32_t (&w)[32], const float4* yf, int valid) {
+__device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[16], uint32_t (&w)[16], const float4* yf, int valid) {
   using namespace tc;
   const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   float acc = 0.f;
 #pragma unroll
-  for (int k4 = 0; k4 < 8; ++k4) {
+  for (int k4 = 0; k4 < 4; ++k4) {
     const float4 y4 = yf[k4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -250,9 +275,9 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(D1_FULL + b), 1);
-      mbar_init(bar(R_FULL + b), 256);
+      mbar_init(bar(R_FULL + b), 128 * kTcSub);
       mbar_init(bar(G_FULL + b), 1);
-      mbar_init(bar(G_FREE + b), 256);
+      mbar_init(bar(G_FREE + b), 128 * kTcSub);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -265,29 +290,28 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + Lay::kOffTmemPtr);
 
-  const bool is_epi = warp >= 4 && warp < 12;
+  const bool is_epi = warp >= 4 && warp < 4 + 4 * kTcSub;
   const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-  const int half = (warp - 4) >> 2;                 // epilogue: which 32 rows of a tile / which 32 G columns
+  const int sub = (warp - 4) >> 2;                  // epilogue: which 16 rows of a tile / which 16 G columns
   const int ci = quarter * 32 + lane;               // chain within the group == TMEM lane
   const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
 
-  // beta of this chain group -> TMEM (A operand of MMA1): half 0 writes the TF32 hi part,
-  // half 1 the remainder beta - hi
+  // beta of this chain group -> TMEM (A operand of MMA1): epilogue warps sub 0,1 write the
+  // TF32 hi part (32 columns each), sub 2,3 the remainder beta - hi
   if (is_epi) {
     const int chain = cg * kTcChains + ci;
     const double* bsrc = a.beta_base + (long long)chain * a.beta_stride;
-#pragma unroll 1
-    for (int ch = 0; ch < P / 32; ++ch) {
-      uint32_t v[32];
+    const bool hi = sub < 2;
+    const int c0 = (sub & 1) * 32;
+    uint32_t v[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int col = ch * 32 + k;
-        const double b = (chain < a.C && col < a.p) ? bsrc[col] : 0.0;
-        const float bh = trunc_tf32((float)b);
-        v[k] = __float_as_uint(half == 0 ? bh : (float)(b - (double)bh));
-      }
-      tmem_st32(tmem + lane_addr + (half == 0 ? Lay::kColBh : Lay::kColBl) + ch * 32, v);
+    for (int k = 0; k < 32; ++k) {
+      const int col = c0 + k;
+      const double b = (chain < a.C && col < a.p) ? bsrc[col] : 0.0;
+      const float bh = trunc_tf32((float)b);
+      v[k] = __float_as_uint(hi ? bh : (float)(b - (double)bh));
     }
+    tmem_st32(tmem + lane_addr + (hi ? Lay::kColBh : Lay::kColBl) + c0, v);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -312,59 +336,66 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (TMEM), B = X rows (K-major)
-      constexpr uint32_t idesc2 = instr_desc(kTcChains, P, 0, 1);         // A = R (TMEM), B = X (MN-major)
-      auto issue_mma2 = [&](int j) {
-        const int s = j % NS, b = j & 1, g = j / kFlush, gb = g & 1;
-        mbar_wait(bar(R_FULL + b), (j >> 1) & 1);
-        tc_fence_after();
-        const bool first_of_group = (j % kFlush) == 0;
-        if (first_of_group && g >= 2) { mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1); tc_fence_after(); }
-        const uint32_t xs = base + s * Lay::kStageBytes;
-        const uint32_t d_t = tmem + Lay::kColG + gb * P;
+    // ===================== MMA issuer.  The whole warp stays converged (so descriptors live in
+    // uniform registers); one elected lane issues the tcgen05.mma / commit instructions.
+    constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (TMEM), B = X rows (K-major)
+    constexpr uint32_t idesc2 = instr_desc(kTcChains, P, 0, 1);         // A = R (TMEM), B = X (MN-major)
+    auto issue_mma2 = [&](int j) {
+      const int s = j % NS, b = j & 1, g = j / kFlush, gb = g & 1;
+      mbar_wait(bar(R_FULL + b), (j >> 1) & 1);
+      const bool first_of_group = (j % kFlush) == 0;
+      if (first_of_group && g >= 2) mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t xs = base + s * Lay::kStageBytes;
+      // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
+      // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
+      const uint64_t dm = smem_desc(xs + Lay::kOffXm, Lay::kXBoxBytes, 512u, 1u);
+      const uint64_t dlm = smem_desc(xs + Lay::kOffXlm, Lay::kXBoxBytes, 512u, 1u);
+      const uint32_t rh = tmem + Lay::kColD1 + b * kTcRows, rl = tmem + Lay::kColRl + b * kTcRows;
+      const uint32_t d_t = tmem + Lay::kColG + gb * P;
+      const uint32_t acc0 = first_of_group ? 0u : 1u;
+      if (elect_one()) {
 #pragma unroll
-        for (int hl = 0; hl < 3; ++hl) {      // Rh.Xh, Rh.Xl, Rl.Xh
-          const uint32_t a_t = tmem + (hl == 2 ? Lay::kColRl : Lay::kColD1) + b * kTcRows;
-          const uint32_t xb = xs + (hl == 1 ? Lay::kOffXlm : Lay::kOffXm);
+        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dm + (uint64_t)(q * 64), idesc2, q == 0 ? acc0 : 1u);
 #pragma unroll
-          for (int q = 0; q < RQ; ++q) {
-            // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
-            // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
-            const uint64_t bdesc = smem_desc(xb + q * 1024u, Lay::kXBoxBytes, 512u, 1u);
-            mma_ts(d_t, a_t + q * 8, bdesc, idesc2, (first_of_group && hl == 0 && q == 0) ? 0u : 1u);
-          }
-        }
+        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dlm + (uint64_t)(q * 64), idesc2, 1u);
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rl + q * 8, dm + (uint64_t)(q * 64), idesc2, 1u);
         tc_commit(bar(X_EMPTY + s));                 // stage s and eta/R buffer b are free again
         if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL + gb));
-      };
-      for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i % NS, b = i & 1;
-        mbar_wait(bar(X_FULL + s), (i / NS) & 1);
-        mbar_wait(bar(XL_FULL + s), (i / NS) & 1);
-        tc_fence_after();
-        const uint32_t xs = base + s * Lay::kStageBytes;
-        const uint32_t d1 = tmem + Lay::kColD1 + b * kTcRows;
-        // eta' = Bh.Xh' + Bh.Xl' + Bl.Xh'
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t at = tmem + (term == 2 ? Lay::kColBl : Lay::kColBh);
-          const uint32_t xb = xs + (term == 1 ? Lay::kOffXlk : Lay::kOffXk);
-#pragma unroll
-          for (int q = 0; q < KQ; ++q) {
-            const uint32_t koff = (q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u;
-            mma_ts(d1, at + q * 8, smem_desc(xb + koff, 16u, 1024u), idesc1, (term == 0 && q == 0) ? 0u : 1u);
-          }
-        }
-        tc_commit(bar(D1_FULL + b));
-        if (i > 0) issue_mma2(i - 1);
       }
-      if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
+      __syncwarp();
+    };
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i % NS, b = i & 1;
+      mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+      mbar_wait(bar(XL_FULL + s), (i / NS) & 1);
+      tc_fence_after();
+      const uint32_t xs = base + s * Lay::kStageBytes;
+      const uint64_t dk = smem_desc(xs + Lay::kOffXk, 16u, 1024u);
+      const uint64_t dlk = smem_desc(xs + Lay::kOffXlk, 16u, 1024u);
+      const uint32_t d1 = tmem + Lay::kColD1 + b * kTcRows;
+      const uint32_t bh = tmem + Lay::kColBh, bl = tmem + Lay::kColBl;
+      if (elect_one()) {
+        // eta' = Bh.Xh' + Bh.Xl' + Bl.Xh'; k-chunk q lives in box q/4 at byte (q%4)*32 of the 128B row
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+          mma_ts(d1, bh + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, q == 0 ? 0u : 1u);
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+          mma_ts(d1, bh + q * 8, dlk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+          mma_ts(d1, bl + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+        tc_commit(bar(D1_FULL + b));
+      }
+      __syncwarp();
+      if (i > 0) issue_mma2(i - 1);
     }
-  } else if (warp >= 12) {
+    if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
+  } else if (warp >= 4 + 4 * kTcSub) {
     // ===================== converters: Xl = X - trunc_tf32(X) (same swizzled offsets), y -> float
-    const int ct = tid - 384;
+    const int ct = tid - 32 * (4 + 4 * kTcSub);
     for (int i = 0; i < ntiles_mine; ++i) {
       const int s = i % NS;
       mbar_wait(bar(X_FULL + s), (i / NS) & 1);
@@ -387,45 +418,45 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       mbar_arrive(bar(XL_FULL + s));
     }
   } else if (is_epi) {
-    // ===================== epilogue: thread = (chain, 32-row half of the tile)
+    // ===================== epilogue: thread = (chain, 16-row slice of the tile)
     double ll_acc = 0.0;
-    double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)(P + 2) * kTcChains;
+    constexpr int PR = P + kTcSub;   // partial rows: kTcSub log-likelihood slots, then the gradient
+    double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)PR * kTcChains;
     // flush gradient group g (TMEM fp32 accumulator) into the float64 partial sums;
-    // this thread owns 32 of the P columns of its chain
+    // this thread owns 16 of the P columns of its chain
     auto flush = [&](int g) {
       const int gb = g & 1;
       mbar_wait(bar(G_FULL + gb), (g >> 1) & 1);
       tc_fence_after();
-      uint32_t gv[32];
-      tmem_ld32(tmem + lane_addr + Lay::kColG + gb * P + half * 32, gv);
+      uint32_t gv[16];
+      tmem_ld16(tmem + lane_addr + Lay::kColG + gb * P + sub * 16, gv);
       tc_fence_before();
       mbar_arrive(bar(G_FREE + gb));
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        double* dst = part + (size_t)(2 + half * 32 + k) * kTcChains + ci;
+      for (int k = 0; k < 16; ++k) {
+        double* dst = part + (size_t)(kTcSub + sub * 16 + k) * kTcChains + ci;
         const double add = (double)__uint_as_float(gv[k]);
         *dst = (g == 0) ? add : (*dst + add);
       }
     };
     for (int i = 0; i < ntiles_mine; ++i) {
       const int s = i % NS, b = i & 1;
-      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + half * 32;
+      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + sub * 16;
       mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
       tc_fence_after();
-      const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + half * 128);
-      uint32_t v[32];
-      const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + half * 32;
-      tmem_ld32(taddr, v);
+      const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + sub * 64);
+      uint32_t v[16], w[16];
+      const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + sub * 16;
+      tmem_ld16(taddr, v);
       if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + half * 32 + k] = __uint_as_float(v[k]);
+        for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + sub * 16 + k] = __uint_as_float(v[k]);
       }
       float ll_tile;
-      uint32_t w[32];
-      if (row0 + 32 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 32);
+      if (row0 + 16 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 16);
       else ll_tile = tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
-      tmem_st32(taddr, v);
-      tmem_st32(tmem + lane_addr + Lay::kColRl + b * kTcRows + half * 32, w);
+      tmem_st16(taddr, v);
+      tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + sub * 16, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(R_FULL + b));
@@ -433,9 +464,9 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       if ((i % kFlush) == 0 && i > 0) flush(i / kFlush - 1);   // deferred: the group's MMA2s are long done
     }
     if (ntiles_mine > 0) flush((ntiles_mine - 1) / kFlush);
-    part[(size_t)half * kTcChains + ci] = ll_acc;
+    part[(size_t)sub * kTcChains + ci] = ll_acc;
     if (ntiles_mine == 0) {
-      for (int k = 0; k < 32; ++k) part[(size_t)(2 + half * 32 + k) * kTcChains + ci] = 0.0;
+      for (int k = 0; k < 16; ++k) part[(size_t)(kTcSub + sub * 16 + k) * kTcChains + ci] = 0.0;
     }
   }
 
@@ -449,7 +480,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
 
 // One CTA per chain: sum the per-CTA float64 partials over row CTAs in a fixed order,
 // then the common finish (prior, result, sampler update).
-// partials: [row_ctas][groups][P+2][128]; rows 0,1 = the two log-likelihood halves, 2+j = gll_j
+// partials: [row_ctas][groups][P+kTcSub][128]; rows 0..kTcSub-1 = log-likelihood slices, then gll_j
 __global__ void finish_tc_kernel(FinishArgs base, const double* partials, int row_ctas, int groups, int P,
                                  SamplerState* states, const double* beta_base, long long beta_stride,
                                  double* res) {
@@ -466,8 +497,12 @@ __global__ void finish_tc_kernel(FinishArgs base, const double* partials, int ro
   for (int j = threadIdx.x; j <= f.p; j += kBlock) {
     double s = 0.0;
     for (int bx = 0; bx < row_ctas; ++bx) {
-      const double* pb = partials + ((size_t)bx * groups + cg) * (size_t)(P + 2) * kTcChains;
-      s += (j == 0) ? (pb[ci] + pb[kTcChains + ci]) : pb[(size_t)(1 + j) * kTcChains + ci];
+      const double* pb = partials + ((size_t)bx * groups + cg) * (size_t)(P + kTcSub) * kTcChains;
+      if (j == 0) {
+        for (int q = 0; q < kTcSub; ++q) s += pb[(size_t)q * kTcChains + ci];
+      } else {
+        s += pb[(size_t)(kTcSub - 1 + j) * kTcChains + ci];
+      }
     }
     s_sums[j] = s;
   }

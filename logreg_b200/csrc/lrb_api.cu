@@ -654,7 +654,7 @@ int reserve_tc(lrb_handle* h, int C) {
   const int groups = (C + kTcChains - 1) / kTcChains;
   const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
   const int gx = std::max(1, std::min(h->sms / groups, ntiles));
-  const size_t need = (size_t)gx * groups * (h->P + 2) * kTcChains;
+  const size_t need = (size_t)gx * groups * (h->P + kTcSub) * kTcChains;
   if (need <= h->partials_tc_cap) return LRB_OK;
   if (h->partials_tc) cudaFree(h->partials_tc);
   h->partials_tc = nullptr; h->partials_tc_cap = 0;
@@ -669,7 +669,7 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   const int groups = (C + kTcChains - 1) / kTcChains;
   const int ntiles = (int)((h->n + kTcRows - 1) / kTcRows);
   const int gx = std::max(1, std::min(h->sms / groups, ntiles));
-  const size_t need = (size_t)gx * groups * (h->P + 2) * kTcChains;
+  const size_t need = (size_t)gx * groups * (h->P + kTcSub) * kTcChains;
   if (need > h->partials_tc_cap) return fail(h, LRB_E_STATE, "tensor-core scratch not reserved (internal error)");
   EvalTcArgs a{};
   a.y = h->y; a.n = h->n; a.ntiles = ntiles;
