@@ -41,6 +41,9 @@ WORKLOADS = {
     "c3": dict(sampler="hmc", n=100_000_000, p=64, mode="fp32", L=20, desc="HMC L=20 diag mass, n=1e8 p=64 fp32 X"),
     "c2": dict(sampler="mala", n=1_000_000, p=32, mode="fp32", L=1, desc="MALA diag precond, n=1e6 p=32 fp32 X"),
     "c5": dict(sampler="ul", n=400_000_000, p=128, mode="fp64", L=1, desc="UL, n=4e8 p=128 fp64 X (needs >= 3 GPUs)"),
+    # config 4: many chains, X replicated, chains sharded over the GPUs, no collective
+    "c4": dict(sampler="mala", n=1_000_000, p=64, mode="fp32", L=1, chains=4096,
+               desc="4096 MALA chains, n=1e6 p=64 fp32 X (tcgen05 3xTF32 many-chain kernel)"),
 }
 SAMPLE_ROWS = 1_000_000     # rows of the same workload the CPU arm is timed on
 
@@ -159,6 +162,62 @@ def time_cpu(w, n_full, steps, warmup, budget_s=None):
                       f"time scaled x{scale:g} to n={n_full} (linear in n)"}
 
 
+def bench_chains(args, w, prob, kern, bt, rank, world, local, barrier, config, metric):
+    """Config 4: C chains in lock-step per GPU (tensor-core many-chain kernel), chains sharded
+    over the ranks with no collective. A step = one MALA iteration of every chain."""
+    import torch
+    import torch.distributed as dist
+    import logreg_b200 as lr
+    K, W = args.steps, max(args.warmup, 1)
+    n, p, C = w["n"], w["p"], w["chains"]
+    c_lo, c_hi = (rank * C) // world, ((rank + 1) * C) // world
+    Cl = c_hi - c_lo
+    sd = 2.2 / np.sqrt(n)
+    inits = bt + 0.5 * sd * np.random.RandomState(100 + rank).randn(Cl, p)
+    prob.run_chains(kern, inits, 1, W, seed=7 + rank)
+    inf0 = prob.info()
+    barrier()
+    t0 = time.perf_counter()
+    mats, acc = prob.run_chains(kern, inits, 1, K, seed=7 + rank)     # host inits in, host samples out
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    inf1 = prob.info()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    value = C * K / dt
+    flops = 4.0 * n * p * Cl * (K + 1)             # algorithmic (1-pass) flops on this rank, incl. the init evaluation
+    peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2
+    line = {"metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+            "vs_baseline": None, "dtype": "tf32x3", "data": "synthetic",
+            "config": dict(config, chains=C, chains_per_gpu=Cl, parallelism=f"chain-sharded x{world}", l2="X (256 MB) exceeds L2 (126 MB)"),
+            "chain_iters_per_s": value, "accept_rate": float(acc.mean() / K),
+            "roofline": {"bound": "tensor", "achieved": flops / dt / 1e12, "peak": peak_tf32, "unit": "TFLOP/s",
+                         "frac": flops / dt / 1e12 / peak_tf32, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense runs at half the bf16 rate)",
+                         "note": "algorithmic 4*n*p*C flops per all-chain evaluation; the 3xTF32 kernel executes 3x that on the "
+                                 "tensor pipe and is co-limited by 3 MUFU ops per (row, chain) element"},
+            "cpu_baseline": None,
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": Cl * p * 8 / K, "d2h_bytes_per_step": Cl * p * 8,
+                    "note": "timed through Problem.run_chains (host inits in, host samples out)"},
+            "gpu_launches": int(inf1["kernel_launches"] - inf0["kernel_launches"]), "clocks": None}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ---------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -210,11 +269,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, p = w["n"], w["p"]
-    lo, hi = lrd.shard_rows(n, rank, world)
+    lo, hi = (0, n) if "chains" in w else lrd.shard_rows(n, rank, world)
     prob = lr.Problem(local)
     prob.n_global = n
     bt = prob.gen_synthetic(hi - lo, p, mode=w["mode"], seed=42, row_offset=lo)
-    if world > 1:
+    if world > 1 and "chains" not in w:
         lrd.init_comm(prob, args.comm)
     h = step_size(w, n)
     if w["sampler"] == "hmc":
@@ -228,6 +287,9 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if "chains" in w:
+        return bench_chains(args, w, prob, kern, bt, rank, world, local, barrier, config, metric)
 
     def maxr(x):
         if world == 1:
