@@ -149,15 +149,11 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   static_assert(S % SPR == 0 && SG >= 1, "row too wide for the batch");
   static_assert((1 << LOG_L) == L && (1 << LOG_SG) == SG, "power-of-two tiling");
 
-  __shared__ double red[kWarps][P];
+  __shared__ double red[kWarps][P + 1];
   __shared__ double redll[kWarps];
   __shared__ double tot[P + 1];
   __shared__ double scratch[kWarps];
   __shared__ unsigned int s_ticket;
-
-  // A paused sampler makes surplus graph nodes no-ops (every CTA sees the same phase:
-  // the last CTA only changes it after all CTAs have taken their ticket).
-  if (a.fin.state != nullptr && a.fin.state->phase == PH_PAUSED) return;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_in_row = lane & (L - 1);      // which chunk of the row segment
@@ -166,8 +162,35 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   const long long n = a.n;
   const long long total_chunks = n * CPR;
   const long long nbatch = (n + RB - 1) / RB;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  const long long bt0 = (long long)blockIdx.x * kWarps + warp;
 
-  // this lane's slice of beta (columns (sl*L + t_in_row)*V .. +V)
+  // Programmatic dependent launch: this grid may start while the previous evaluation's last
+  // CTA is still reducing / running the sampler update.  X never changes, so the first batch
+  // is fetched BEFORE waiting for the previous grid (hides launch latency and the DRAM ramp);
+  // everything that depends on it (beta, the pause flag, the partials buffer) comes after.
+  vec v[S];
+  auto load_batch = [&](long long bt) {
+    const long long chunk0 = bt * (S * 32) + lane;
+    if (bt * RB + RB <= n) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[s] = ldg_stream(Xv + chunk0 + s * 32);
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const long long c = chunk0 + s * 32;
+        v[s] = c < total_chunks ? ldg_stream(Xv + c) : zero_vec((vec*)nullptr);
+      }
+    }
+  };
+  if (bt0 < nbatch) load_batch(bt0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // A paused sampler makes surplus graph nodes no-ops (every CTA sees the same phase:
+  // the last CTA only changes it after all CTAs have taken their ticket).
+  if (a.fin.state != nullptr && __ldcg(&a.fin.state->phase) == PH_PAUSED) return;
+
+  // this lane's slice of beta (read through L2: the previous grid's last CTA wrote it) (columns (sl*L + t_in_row)*V .. +V)
   A bh[SPR][V];
   float bl[SPR][V];
 #pragma unroll
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int col = (sl * L + t_in_row) * V + i;
-      const double b = col < a.fin.p ? a.fin.beta[col] : 0.0;
+      const double b = col < a.fin.p ? __ldcg(a.fin.beta + col) : 0.0;
       bh[sl][i] = (A)b;
       bl[sl][i] = (float)(b - (double)bh[sl][i]);   // exactly 0 in FP64 mode
     }
@@ -193,21 +216,9 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
     for (int i = 0; i < V; ++i) acc[sl][i] = 0.0;
   double ll_acc = 0.0;
 
-  const long long nwarps = (long long)gridDim.x * kWarps;
-  for (long long bt = (long long)blockIdx.x * kWarps + warp; bt < nbatch; bt += nwarps) {
-    const long long chunk0 = bt * (S * 32) + lane;
+  for (long long bt = bt0; bt < nbatch; bt += nwarps) {
     const long long row0 = bt * RB;
-    vec v[S];
-    if (row0 + RB <= n) {
-#pragma unroll
-      for (int s = 0; s < S; ++s) v[s] = ldg_stream(Xv + chunk0 + s * 32);
-    } else {
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const long long c = chunk0 + s * 32;
-        v[s] = c < total_chunks ? ldg_stream(Xv + c) : zero_vec((vec*)nullptr);
-      }
-    }
+    if (bt != bt0) load_batch(bt);
     bool y1[M], valid[M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -274,6 +285,8 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
     }
   }
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // streaming done: let the next grid in
+
   // ---- CTA reduction
   if constexpr (GRAD) {
 #pragma unroll
@@ -314,22 +327,31 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   __threadfence();
   if (tid == 0) *a.ticket = 0u;  // re-arm for the next launch (stream-ordered)
 
-  constexpr int NS = 4;                       // interleaved sub-sums per column
+  // warp w sums the partial vectors of CTAs w, w+8, ... (4 independent accumulators keep
+  // 4 L2 loads in flight per lane), lanes stride over the columns; then the 8 warp sums are
+  // added in warp order.  Fixed order => bit-reproducible for a fixed grid.
   constexpr int NC = GRAD ? P + 1 : 1;
-  double* part = &red[0][0];                  // reuse: NS*(P+1) <= kWarps*P doubles
-  static_assert(NS * (P + 1) <= kWarps * P, "scratch too small");
-  for (int idx = tid; idx < NS * NC; idx += kBlock) {
-    const int c = idx % NC, sp = idx / NC;
-    double s = 0.0;
-    for (int b = sp; b < (int)gridDim.x; b += NS) s += __ldcg(a.partials + (size_t)b * (P + 1) + c);
-    part[sp * (P + 1) + c] = s;
+  const int G_ = (int)gridDim.x;
+  for (int c = lane; c < NC; c += 32) {
+    const double* src = a.partials + c;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int bb = warp;
+    for (; bb + 3 * kWarps < G_; bb += 4 * kWarps) {
+      const double v0 = __ldcg(src + (size_t)bb * (P + 1));
+      const double v1 = __ldcg(src + (size_t)(bb + kWarps) * (P + 1));
+      const double v2 = __ldcg(src + (size_t)(bb + 2 * kWarps) * (P + 1));
+      const double v3 = __ldcg(src + (size_t)(bb + 3 * kWarps) * (P + 1));
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; bb < G_; bb += kWarps) s0 += __ldcg(src + (size_t)bb * (P + 1));
+    red[warp][c] = (s0 + s1) + (s2 + s3);
   }
   __syncthreads();
   for (int c = tid; c <= P; c += kBlock) {
     double s = 0.0;
     if (c < NC) {
 #pragma unroll
-      for (int sp = 0; sp < NS; ++sp) s += part[sp * (P + 1) + c];
+      for (int w = 0; w < kWarps; ++w) s += red[w][c];
     }
     tot[c] = s;
   }

@@ -209,9 +209,17 @@ __global__ void __launch_bounds__(kBlock, 1) eval_mc_kernel(const EvalMcArgs a) 
   // last CTA: fixed-order sum of the CTA partials for each active chain
   for (int idx = tid; idx < a.nc_active * (P + 1); idx += kBlock) {
     const int c = idx / (P + 1), col = idx % (P + 1);
-    double s = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(a.partials + ((size_t)b * NC + c) * (P + 1) + col);
-    if (col <= a.p) a.sums[(size_t)(a.chain0 + c) * kSumStride + col] = s;
+    const double* src = a.partials + (size_t)c * (P + 1) + col;
+    const size_t stride = (size_t)NC * (P + 1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < (int)gridDim.x; b += 4) {
+      const double v0 = __ldcg(src + (size_t)b * stride), v1 = __ldcg(src + (size_t)(b + 1) * stride);
+      const double v2 = __ldcg(src + (size_t)(b + 2) * stride), v3 = __ldcg(src + (size_t)(b + 3) * stride);
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * stride);
+    if (col <= a.p) a.sums[(size_t)(a.chain0 + c) * kSumStride + col] = (s0 + s1) + (s2 + s3);
   }
 }
 

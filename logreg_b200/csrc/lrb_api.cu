@@ -176,7 +176,8 @@ struct lrb_handle {
   CUtensorMap xmap_k{}, xmap_mn{};
   double* partials_tc = nullptr; size_t partials_tc_cap = 0;
   float* dbg_eta = nullptr;
-  int tc_min_chains = 32;
+  int tc_min_chains = 12;   // measured crossover, profiles/r1_many_chain_threshold.txt
+  bool pdl = true;
 
   long long kernel_launches = 0, eval_launches = 0;
 };
@@ -278,6 +279,7 @@ int configure(lrb_handle* h) {
     }
   }
   if (const char* env = getenv("LRB_TC_MIN_CHAINS")) h->tc_min_chains = atoi(env);
+  if (const char* env = getenv("LRB_PDL")) h->pdl = atoi(env) != 0;
   return LRB_OK;
 }
 
@@ -334,7 +336,19 @@ int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_
   a.fuse_finish = nccl_mode ? 0 : 1;
   EvalFn fn = want_grad ? h->kern.grad : h->kern.nograd;
   const int grid = want_grad ? h->grid : h->grid_nograd;
-  fn<<<grid, kBlock, 0, h->stream>>>(a);
+  if (h->pdl && !nccl_mode) {
+    // programmatic dependent launch: the grid may start while the previous evaluation's last CTA
+    // is still in its reduction / sampler update (see the prologue of eval_kernel)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(h, cudaLaunchKernelEx(&cfg, fn, a));
+  } else {
+    fn<<<grid, kBlock, 0, h->stream>>>(a);
+  }
   CK(h, cudaGetLastError());
   h->kernel_launches++;
   h->eval_launches++;
