@@ -17,8 +17,8 @@
 //               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 3-stage ring.
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
 //   warp 2      TMEM allocator (512 columns: eta/R x2, gradient x2, beta hi, beta lo).
-//   warps 4-19  epilogue: thread = (chain = TMEM lane, 16-row slice of the tile); four
-//               warps per scheduler keep the MUFU pipe (3 ops per element) busy.
+//   warps 4-19  epilogue: thread = chain = TMEM lane; two groups of 8 warps take alternate
+//               tiles so two tiles are always in flight on the MUFU pipe (3 ops per element).
 //               tcgen05.ld eta, link functions, log-likelihood into a per-thread
 //               accumulator (no cross-thread reduction: a thread owns its chain),
 //               residual r rounded to TF32 and written back IN PLACE with tcgen05.st,
@@ -59,6 +59,7 @@ struct EvalTcArgs {
   double* partials;            // [gridDim.x][gridDim.y][P+kTcSub][128]: ll slices, then gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
   float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
+  int dbg_flags;               // development knobs (0 in production): 1 skip link math, 2 single-term MMAs
 };
 
 namespace tc {
@@ -275,7 +276,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(D1_FULL + b), 1);
-      mbar_init(bar(R_FULL + b), 128 * kTcSub);
+      mbar_init(bar(R_FULL + b), 64 * kTcSub);   // one epilogue group (8 warps) per eta/R buffer
       mbar_init(bar(G_FULL + b), 1);
       mbar_init(bar(G_FREE + b), 128 * kTcSub);
     }
@@ -357,10 +358,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dm + (uint64_t)(q * 64), idesc2, q == 0 ? acc0 : 1u);
+        if (!(a.dbg_flags & 2)) {
 #pragma unroll
-        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dlm + (uint64_t)(q * 64), idesc2, 1u);
+          for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dlm + (uint64_t)(q * 64), idesc2, 1u);
 #pragma unroll
-        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rl + q * 8, dm + (uint64_t)(q * 64), idesc2, 1u);
+          for (int q = 0; q < RQ; ++q) mma_ts(d_t, rl + q * 8, dm + (uint64_t)(q * 64), idesc2, 1u);
+        }
         tc_commit(bar(X_EMPTY + s));                 // stage s and eta/R buffer b are free again
         if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL + gb));
       }
@@ -381,12 +384,14 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
 #pragma unroll
         for (int q = 0; q < KQ; ++q)
           mma_ts(d1, bh + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, q == 0 ? 0u : 1u);
+        if (!(a.dbg_flags & 2)) {
 #pragma unroll
-        for (int q = 0; q < KQ; ++q)
-          mma_ts(d1, bh + q * 8, dlk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+          for (int q = 0; q < KQ; ++q)
+            mma_ts(d1, bh + q * 8, dlk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
 #pragma unroll
-        for (int q = 0; q < KQ; ++q)
-          mma_ts(d1, bl + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+          for (int q = 0; q < KQ; ++q)
+            mma_ts(d1, bl + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+        }
         tc_commit(bar(D1_FULL + b));
       }
       __syncwarp();
@@ -418,7 +423,11 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       mbar_arrive(bar(XL_FULL + s));
     }
   } else if (is_epi) {
-    // ===================== epilogue: thread = (chain, 16-row slice of the tile)
+    // ===================== epilogue: thread = chain (TMEM lane).  The 16 warps form two
+    // groups that take alternate tiles (group = eta/R buffer), so two tiles are always in
+    // flight on the MUFU pipe and a group's wait for its next eta overlaps the other group's
+    // work; inside a group a thread owns a 32-row half of the tile, processed 16 rows at a time.
+    const int grp = sub & 1, hf = sub >> 1;
     double ll_acc = 0.0;
     constexpr int PR = P + kTcSub;   // partial rows: kTcSub log-likelihood slots, then the gradient
     double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)PR * kTcChains;
@@ -439,31 +448,43 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         *dst = (g == 0) ? add : (*dst + add);
       }
     };
-    for (int i = 0; i < ntiles_mine; ++i) {
-      const int s = i % NS, b = i & 1;
-      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + sub * 16;
+    int next_flush = 0;
+    for (int i = grp; i < ntiles_mine; i += 2) {
+      const int s = i % NS, b = grp;
       mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
       tc_fence_after();
-      const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + sub * 64);
-      uint32_t v[16], w[16];
-      const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + sub * 16;
-      tmem_ld16(taddr, v);
-      if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
+      float ll_tile = 0.f;
+#pragma unroll 1
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int r_off = hf * 32 + c2 * 16;
+        const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + r_off;
+        const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + r_off * 4);
+        uint32_t v[16], w[16];
+        const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + r_off;
+        tmem_ld16(taddr, v);
+        if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + sub * 16 + k] = __uint_as_float(v[k]);
+          for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + r_off + k] = __uint_as_float(v[k]);
+        }
+        if (a.dbg_flags & 1) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { w[k] = v[k] & 0x1fffu; v[k] &= 0xffffe000u; }
+        } else if (row0 + 16 <= a.n) ll_tile += tc_link_chunk<false>(v, w, yf, 16);
+        else ll_tile += tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
+        tmem_st16(taddr, v);
+        tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + r_off, w);
       }
-      float ll_tile;
-      if (row0 + 16 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 16);
-      else ll_tile = tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
-      tmem_st16(taddr, v);
-      tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + sub * 16, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(R_FULL + b));
       ll_acc += (double)ll_tile;
-      if ((i % kFlush) == 0 && i > 0) flush(i / kFlush - 1);   // deferred: the group's MMA2s are long done
+      // deferred flushes: groups whose last MMA2 was issued at least one tile ago
+      while (next_flush < i / kFlush) flush(next_flush++);
     }
-    if (ntiles_mine > 0) flush((ntiles_mine - 1) / kFlush);
+    if (ntiles_mine > 0) {
+      const int g_last = (ntiles_mine - 1) / kFlush;
+      while (next_flush <= g_last) flush(next_flush++);
+    }
     part[(size_t)sub * kTcChains + ci] = ll_acc;
     if (ntiles_mine == 0) {
       for (int k = 0; k < 16; ++k) part[(size_t)(kTcSub + sub * 16 + k) * kTcChains + ci] = 0.0;
