@@ -168,7 +168,7 @@ def bench_chains(args, w, prob, kern, bt, rank, world, local, barrier, config, m
     import torch
     import torch.distributed as dist
     import logreg_b200 as lr
-    K, W = args.steps, max(args.warmup, 1)
+    K, W = max(args.steps, 40), max(args.warmup, 10)   # ~7 ms per step at 4096 chains: keep the timed region >= 0.25 s
     n, p, C = w["n"], w["p"], w["chains"]
     c_lo, c_hi = (rank * C) // world, ((rank + 1) * C) // world
     Cl = c_hi - c_lo

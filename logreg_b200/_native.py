@@ -77,7 +77,7 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    return os.environ.get("LRB_LIBRARY") or _build.LIB   # override: A/B a differently built library
 
 
 def load(build_if_missing: bool = True):

@@ -11,15 +11,14 @@
 //
 // One CTA (768 threads, 1 per SM) owns one group of 128 chains and a strided set of
 // 64-row tiles:
-//   warps 0, 3  TMA producers: the X tile is fetched TWICE (P/32 boxes of 64 rows x 32 floats):
-//               warp 0 with the plain 128-byte swizzle (K-major operand of MMA1) + the 64 y
-//               bytes, warp 3 with the 128B/32B-atom swizzle (the only layout tcgen05 accepts
-//               for an MN-major TF32 operand, needed by MMA2).  Two independent 3-stage
-//               mbarrier rings: a K stage is released right after MMA1, an MN stage after MMA2.
+//   warp 0      TMA producer: the X tile TWICE (P/32 boxes of 64 rows x 32 floats each):
+//               once with the plain 128-byte swizzle (K-major operand of MMA1) and once
+//               with the 128B/32B-atom swizzle (the only layout tcgen05 accepts for an
+//               MN-major TF32 operand, needed by MMA2), + the 64 y bytes; 3-stage ring.
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / commit).
 //   warp 2      TMEM allocator (512 columns: eta/R x2, gradient x2, beta hi, beta lo).
-//   warps 4-19  epilogue: thread = chain = TMEM lane; two groups of 8 warps take alternate
-//               tiles so two tiles are always in flight on the MUFU pipe (3 ops per element).
+//   warps 4-19  epilogue: thread = (chain = TMEM lane, 16-row slice of the tile); four
+//               warps per scheduler keep the MUFU pipe (3 ops per element) busy.
 //               tcgen05.ld eta, link functions, log-likelihood into a per-thread
 //               accumulator (no cross-thread reduction: a thread owns its chain),
 //               residual r rounded to TF32 and written back IN PLACE with tcgen05.st,
@@ -60,7 +59,6 @@ struct EvalTcArgs {
   double* partials;            // [gridDim.x][gridDim.y][P+kTcSub][128]: ll slices, then gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
   float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
-  int dbg_flags;               // development knobs (0 in production): 1 skip link math, 2 single-term MMAs
 };
 
 namespace tc {
@@ -188,19 +186,17 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 
 template <int P>
 struct TcLayout {
-  // Two independent smem rings: the K-major copy of a tile (operand of MMA1) is released as soon
-  // as MMA1 has read it, the MN-major copy (operand of MMA2) only after MMA2 -- one epilogue later.
-  static constexpr int kStagesK = 3, kStagesM = 3, kSlotsY = 8;
+  static constexpr int kStages = 3;
   static constexpr int kBoxes = P / 32;                        // 32-float (128-byte) column boxes per tile
   static constexpr uint32_t kXBoxBytes = kTcRows * 128;        // X box: 64 rows x 128 bytes
   static constexpr uint32_t kXTileBytes = kBoxes * kXBoxBytes;
-  static constexpr uint32_t kStageBytes = 2 * kXTileBytes;     // [X | Xl] of one swizzle flavour
-  static constexpr uint32_t kOffK = 0;                                   // K ring:  [Xk | Xlk] x kStagesK
-  static constexpr uint32_t kOffM = kStagesK * kStageBytes;              // MN ring: [Xm | Xlm] x kStagesM
-  static constexpr uint32_t kOffY = kOffM + kStagesM * kStageBytes;      // raw y bytes, 128-byte slot per K stage
-  static constexpr uint32_t kOffYf = kOffY + kStagesK * 128;             // y as float, 256 bytes x kSlotsY
-  static constexpr uint32_t kOffBar = kOffYf + kSlotsY * 256;
-  static constexpr uint32_t kNumBar = 3 * kStagesK + 3 * kStagesM + 8;
+  // stage: [Xk | Xlk | Xm | Xlm]  (k = SW128 copy for MMA1, m = SW128/32B-atom copy for MMA2)
+  static constexpr uint32_t kOffXk = 0, kOffXlk = kXTileBytes, kOffXm = 2 * kXTileBytes, kOffXlm = 3 * kXTileBytes;
+  static constexpr uint32_t kStageBytes = 4 * kXTileBytes;
+  static constexpr uint32_t kOffY = kStages * kStageBytes;      // raw y bytes, one 128-byte slot per stage
+  static constexpr uint32_t kOffYf = kOffY + kStages * 128;     // y as float, 256 bytes per stage
+  static constexpr uint32_t kOffBar = kOffYf + kStages * 256;
+  static constexpr uint32_t kNumBar = 3 * kStages + 8;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBar * 8;
   static constexpr uint32_t kBytes = kOffTmemPtr + 16;
   static constexpr uint32_t kDynSmem = kBytes + 1024;           // manual 1024-byte alignment slack
@@ -253,7 +249,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   using namespace tc;
   using Lay = TcLayout<P>;
   static_assert(P == 64, "tensor-core path: P = 64");
-  constexpr int NSK = Lay::kStagesK, NSM = Lay::kStagesM, NY = Lay::kSlotsY;
+  constexpr int NS = Lay::kStages;
   constexpr int KQ = P / 8;            // MMA1 k-chunks (TF32 UMMA_K = 8)
   constexpr int RQ = kTcRows / 8;      // MMA2 k-chunks
 
@@ -268,24 +264,18 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   const int ntiles_mine = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   auto bar = [&](int i) { return base + Lay::kOffBar + 8u * i; };
-  constexpr int K_FULL = 0, KL_FULL = NSK, K_EMPTY = 2 * NSK, M_FULL = 3 * NSK, ML_FULL = 3 * NSK + NSM,
-                M_EMPTY = 3 * NSK + 2 * NSM, D1_FULL = 3 * NSK + 3 * NSM, R_FULL = D1_FULL + 2,
-                G_FULL = D1_FULL + 4, G_FREE = D1_FULL + 6;
+  constexpr int X_FULL = 0, XL_FULL = NS, X_EMPTY = 2 * NS, D1_FULL = 3 * NS, R_FULL = 3 * NS + 2,
+                G_FULL = 3 * NS + 4, G_FREE = 3 * NS + 6;
 
   if (tid == 0) {
-    for (int s = 0; s < NSK; ++s) {
-      mbar_init(bar(K_FULL + s), 1);
-      mbar_init(bar(KL_FULL + s), 64);
-      mbar_init(bar(K_EMPTY + s), 1);
-    }
-    for (int s = 0; s < NSM; ++s) {
-      mbar_init(bar(M_FULL + s), 1);
-      mbar_init(bar(ML_FULL + s), 64);
-      mbar_init(bar(M_EMPTY + s), 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bar(X_FULL + s), 1);
+      mbar_init(bar(XL_FULL + s), 128);
+      mbar_init(bar(X_EMPTY + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(D1_FULL + b), 1);
-      mbar_init(bar(R_FULL + b), 64 * kTcSub);   // one epilogue group (8 warps) per eta/R buffer
+      mbar_init(bar(R_FULL + b), 128 * kTcSub);
       mbar_init(bar(G_FULL + b), 1);
       mbar_init(bar(G_FREE + b), 128 * kTcSub);
     }
@@ -329,32 +319,20 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
   tc_fence_after();
 
   if (warp == 0) {
-    // ===================== TMA producer, K ring: SW128 copy of the tile + its y bytes
+    // ===================== TMA producer
     if (lane == 0) {
       for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i % NSK;
+        const int s = i % NS;
         const int tile = blockIdx.x + i * gridDim.x;
-        mbar_wait(bar(K_EMPTY + s), ((i / NSK) & 1) ^ 1);
-        mbar_expect_tx(bar(K_FULL + s), Lay::kXTileBytes + (uint32_t)kTcRows);
-        const uint32_t dst = base + Lay::kOffK + s * Lay::kStageBytes;
+        mbar_wait(bar(X_EMPTY + s), ((i / NS) & 1) ^ 1);
+        mbar_expect_tx(bar(X_FULL + s), 2u * Lay::kXTileBytes + (uint32_t)kTcRows);
+        const uint32_t dst = base + s * Lay::kStageBytes;
 #pragma unroll
-        for (int b = 0; b < Lay::kBoxes; ++b)
-          tma_load_2d(dst + b * Lay::kXBoxBytes, &xmap_k, bar(K_FULL + s), 32 * b, tile * kTcRows);
-        bulk_load(base + Lay::kOffY + s * 128, a.y + (long long)tile * kTcRows, (uint32_t)kTcRows, bar(K_FULL + s));
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== TMA producer, MN ring: SW128/32B-atom copy of the tile
-    if (lane == 0) {
-      for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i % NSM;
-        const int tile = blockIdx.x + i * gridDim.x;
-        mbar_wait(bar(M_EMPTY + s), ((i / NSM) & 1) ^ 1);
-        mbar_expect_tx(bar(M_FULL + s), Lay::kXTileBytes);
-        const uint32_t dst = base + Lay::kOffM + s * Lay::kStageBytes;
-#pragma unroll
-        for (int b = 0; b < Lay::kBoxes; ++b)
-          tma_load_2d(dst + b * Lay::kXBoxBytes, &xmap_mn, bar(M_FULL + s), 32 * b, tile * kTcRows);
+        for (int b = 0; b < Lay::kBoxes; ++b) {
+          tma_load_2d(dst + Lay::kOffXk + b * Lay::kXBoxBytes, &xmap_k, bar(X_FULL + s), 32 * b, tile * kTcRows);
+          tma_load_2d(dst + Lay::kOffXm + b * Lay::kXBoxBytes, &xmap_mn, bar(X_FULL + s), 32 * b, tile * kTcRows);
+        }
+        bulk_load(base + Lay::kOffY + s * 128, a.y + (long long)tile * kTcRows, (uint32_t)kTcRows, bar(X_FULL + s));
       }
     }
   } else if (warp == 1) {
@@ -363,43 +341,39 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
     constexpr uint32_t idesc1 = instr_desc(kTcChains, kTcRows, 0, 0);   // A = beta (TMEM), B = X rows (K-major)
     constexpr uint32_t idesc2 = instr_desc(kTcChains, P, 0, 1);         // A = R (TMEM), B = X (MN-major)
     auto issue_mma2 = [&](int j) {
-      const int s = j % NSM, b = j & 1, g = j / kFlush, gb = g & 1;
-      mbar_wait(bar(M_FULL + s), (j / NSM) & 1);
-      mbar_wait(bar(ML_FULL + s), (j / NSM) & 1);
+      const int s = j % NS, b = j & 1, g = j / kFlush, gb = g & 1;
       mbar_wait(bar(R_FULL + b), (j >> 1) & 1);
       const bool first_of_group = (j % kFlush) == 0;
       if (first_of_group && g >= 2) mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1);
       tc_fence_after();
-      const uint32_t xs = base + Lay::kOffM + s * Lay::kStageBytes;
+      const uint32_t xs = base + s * Lay::kStageBytes;
       // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
       // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
-      const uint64_t dm = smem_desc(xs, Lay::kXBoxBytes, 512u, 1u);
-      const uint64_t dlm = smem_desc(xs + Lay::kXTileBytes, Lay::kXBoxBytes, 512u, 1u);
+      const uint64_t dm = smem_desc(xs + Lay::kOffXm, Lay::kXBoxBytes, 512u, 1u);
+      const uint64_t dlm = smem_desc(xs + Lay::kOffXlm, Lay::kXBoxBytes, 512u, 1u);
       const uint32_t rh = tmem + Lay::kColD1 + b * kTcRows, rl = tmem + Lay::kColRl + b * kTcRows;
       const uint32_t d_t = tmem + Lay::kColG + gb * P;
       const uint32_t acc0 = first_of_group ? 0u : 1u;
       if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dm + (uint64_t)(q * 64), idesc2, q == 0 ? acc0 : 1u);
-        if (!(a.dbg_flags & 2)) {
 #pragma unroll
-          for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dlm + (uint64_t)(q * 64), idesc2, 1u);
+        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rh + q * 8, dlm + (uint64_t)(q * 64), idesc2, 1u);
 #pragma unroll
-          for (int q = 0; q < RQ; ++q) mma_ts(d_t, rl + q * 8, dm + (uint64_t)(q * 64), idesc2, 1u);
-        }
-        tc_commit(bar(M_EMPTY + s));                 // MN stage s and eta/R buffer b are free again
+        for (int q = 0; q < RQ; ++q) mma_ts(d_t, rl + q * 8, dm + (uint64_t)(q * 64), idesc2, 1u);
+        tc_commit(bar(X_EMPTY + s));                 // stage s and eta/R buffer b are free again
         if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL + gb));
       }
       __syncwarp();
     };
     for (int i = 0; i < ntiles_mine; ++i) {
-      const int s = i % NSK, b = i & 1;
-      mbar_wait(bar(K_FULL + s), (i / NSK) & 1);
-      mbar_wait(bar(KL_FULL + s), (i / NSK) & 1);
+      const int s = i % NS, b = i & 1;
+      mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+      mbar_wait(bar(XL_FULL + s), (i / NS) & 1);
       tc_fence_after();
-      const uint32_t xs = base + Lay::kOffK + s * Lay::kStageBytes;
-      const uint64_t dk = smem_desc(xs, 16u, 1024u);
-      const uint64_t dlk = smem_desc(xs + Lay::kXTileBytes, 16u, 1024u);
+      const uint32_t xs = base + s * Lay::kStageBytes;
+      const uint64_t dk = smem_desc(xs + Lay::kOffXk, 16u, 1024u);
+      const uint64_t dlk = smem_desc(xs + Lay::kOffXlk, 16u, 1024u);
       const uint32_t d1 = tmem + Lay::kColD1 + b * kTcRows;
       const uint32_t bh = tmem + Lay::kColBh, bl = tmem + Lay::kColBl;
       if (elect_one()) {
@@ -407,68 +381,44 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
 #pragma unroll
         for (int q = 0; q < KQ; ++q)
           mma_ts(d1, bh + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, q == 0 ? 0u : 1u);
-        if (!(a.dbg_flags & 2)) {
 #pragma unroll
-          for (int q = 0; q < KQ; ++q)
-            mma_ts(d1, bh + q * 8, dlk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
+        for (int q = 0; q < KQ; ++q)
+          mma_ts(d1, bh + q * 8, dlk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
 #pragma unroll
-          for (int q = 0; q < KQ; ++q)
-            mma_ts(d1, bl + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
-        }
+        for (int q = 0; q < KQ; ++q)
+          mma_ts(d1, bl + q * 8, dk + (uint64_t)(((q >> 2) * Lay::kXBoxBytes + (q & 3) * 32u) >> 4), idesc1, 1u);
         tc_commit(bar(D1_FULL + b));
-        tc_commit(bar(K_EMPTY + s));                 // K stage s can be refilled
       }
       __syncwarp();
       if (i > 0) issue_mma2(i - 1);
     }
     if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
   } else if (warp >= 4 + 4 * kTcSub) {
-    // ===================== converters: Xl = X - trunc_tf32(X) at the same (swizzled) offsets.
-    // Warps 20,21 serve the K ring (and turn the y bytes into floats), warps 22,23 the MN ring.
-    const int cw = warp - (4 + 4 * kTcSub);
-    const int ct = (cw & 1) * 32 + lane;            // 0..63 within the pair
-    if (cw < 2) {
-      for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i % NSK;
-        mbar_wait(bar(K_FULL + s), (i / NSK) & 1);
-        reinterpret_cast<float*>(gen + Lay::kOffYf + (i % NY) * 256)[ct] = (float)(gen + Lay::kOffY + s * 128)[ct];
-        const float4* src = reinterpret_cast<const float4*>(gen + Lay::kOffK + s * Lay::kStageBytes);
-        float4* dst = reinterpret_cast<float4*>(gen + Lay::kOffK + s * Lay::kStageBytes + Lay::kXTileBytes);
+    // ===================== converters: Xl = X - trunc_tf32(X) (same swizzled offsets), y -> float
+    const int ct = tid - 32 * (4 + 4 * kTcSub);
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i % NS;
+      mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+      if (ct < kTcRows)
+        reinterpret_cast<float*>(gen + Lay::kOffYf + s * 256)[ct] = (float)(gen + Lay::kOffY + s * 128)[ct];
+#pragma unroll
+      for (int set = 0; set < 2; ++set) {
+        const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXm : Lay::kOffXk));
+        float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXlm : Lay::kOffXlk));
 #pragma unroll 4
-        for (int k = ct; k < (int)(Lay::kXTileBytes / 16); k += 64) {
+        for (int k = ct; k < (int)(Lay::kXTileBytes / 16); k += 128) {
           const float4 x = src[k];
           float4 l;
           l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
           l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
           dst[k] = l;
         }
-        fence_async_smem();
-        mbar_arrive(bar(KL_FULL + s));
       }
-    } else {
-      for (int i = 0; i < ntiles_mine; ++i) {
-        const int s = i % NSM;
-        mbar_wait(bar(M_FULL + s), (i / NSM) & 1);
-        const float4* src = reinterpret_cast<const float4*>(gen + Lay::kOffM + s * Lay::kStageBytes);
-        float4* dst = reinterpret_cast<float4*>(gen + Lay::kOffM + s * Lay::kStageBytes + Lay::kXTileBytes);
-#pragma unroll 4
-        for (int k = ct; k < (int)(Lay::kXTileBytes / 16); k += 64) {
-          const float4 x = src[k];
-          float4 l;
-          l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
-          l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
-          dst[k] = l;
-        }
-        fence_async_smem();
-        mbar_arrive(bar(ML_FULL + s));
-      }
+      fence_async_smem();
+      mbar_arrive(bar(XL_FULL + s));
     }
   } else if (is_epi) {
-    // ===================== epilogue: thread = chain (TMEM lane).  The 16 warps form two
-    // groups that take alternate tiles (group = eta/R buffer), so two tiles are always in
-    // flight on the MUFU pipe and a group's wait for its next eta overlaps the other group's
-    // work; inside a group a thread owns a 32-row half of the tile, processed 16 rows at a time.
-    const int grp = sub & 1, hf = sub >> 1;
+    // ===================== epilogue: thread = (chain, 16-row slice of the tile)
     double ll_acc = 0.0;
     constexpr int PR = P + kTcSub;   // partial rows: kTcSub log-likelihood slots, then the gradient
     double* part = a.partials + ((size_t)blockIdx.x * gridDim.y + cg) * (size_t)PR * kTcChains;
@@ -489,43 +439,31 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         *dst = (g == 0) ? add : (*dst + add);
       }
     };
-    int next_flush = 0;
-    for (int i = grp; i < ntiles_mine; i += 2) {
-      const int b = grp;
+    for (int i = 0; i < ntiles_mine; ++i) {
+      const int s = i % NS, b = i & 1;
+      const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + sub * 16;
       mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
       tc_fence_after();
-      float ll_tile = 0.f;
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int r_off = hf * 32 + c2 * 16;
-        const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + r_off;
-        const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + (i % NY) * 256 + r_off * 4);
-        uint32_t v[16], w[16];
-        const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + r_off;
-        tmem_ld16(taddr, v);
-        if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
+      const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + sub * 64);
+      uint32_t v[16], w[16];
+      const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + sub * 16;
+      tmem_ld16(taddr, v);
+      if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + r_off + k] = __uint_as_float(v[k]);
-        }
-        if (a.dbg_flags & 1) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) { w[k] = v[k] & 0x1fffu; v[k] &= 0xffffe000u; }
-        } else if (row0 + 16 <= a.n) ll_tile += tc_link_chunk<false>(v, w, yf, 16);
-        else ll_tile += tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
-        tmem_st16(taddr, v);
-        tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + r_off, w);
+        for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + sub * 16 + k] = __uint_as_float(v[k]);
       }
+      float ll_tile;
+      if (row0 + 16 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 16);
+      else ll_tile = tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
+      tmem_st16(taddr, v);
+      tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + sub * 16, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(R_FULL + b));
       ll_acc += (double)ll_tile;
-      // deferred flushes: groups whose last MMA2 was issued at least one tile ago
-      while (next_flush < i / kFlush) flush(next_flush++);
+      if ((i % kFlush) == 0 && i > 0) flush(i / kFlush - 1);   // deferred: the group's MMA2s are long done
     }
-    if (ntiles_mine > 0) {
-      const int g_last = (ntiles_mine - 1) / kFlush;
-      while (next_flush <= g_last) flush(next_flush++);
-    }
+    if (ntiles_mine > 0) flush((ntiles_mine - 1) / kFlush);
     part[(size_t)sub * kTcChains + ci] = ll_acc;
     if (ntiles_mine == 0) {
       for (int k = 0; k < 16; ++k) part[(size_t)(kTcSub + sub * 16 + k) * kTcChains + ci] = 0.0;

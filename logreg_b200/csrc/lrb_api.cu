@@ -689,7 +689,6 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   a.y = h->y; a.n = h->n; a.ntiles = ntiles;
   a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
   a.partials = h->partials_tc; a.states = states; a.dbg_eta = h->dbg_eta;
-  if (const char* env = getenv("LRB_TC_DEBUG")) a.dbg_flags = atoi(env);
   dim3 grid(gx, groups);
   eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
   CK(h, cudaGetLastError());
