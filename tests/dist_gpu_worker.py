@@ -58,6 +58,15 @@ def main():
             dist.all_gather(ts, t)
             for o in ts:
                 assert torch.equal(o, ts[0]), (kind, mode, "chains disagree across ranks")
+        # several chains on a row-sharded handle (NCCL: lock-step many-chain kernel; fused P2P:
+        # chain by chain) == the same chains on one GPU
+        k_s = lr.malaKernel(prob.lpost, prob.glp, dt=(0.5 * sd) ** 2, pre=1.0)
+        k_f = lr.malaKernel(full.lpost, full.glp, dt=(0.5 * sd) ** 2, pre=1.0)
+        inits = bt + 0.3 * sd * np.random.RandomState(9).randn(3, p)
+        ms, accs = prob.run_chains(k_s, inits, 1, 8, seed=4)
+        mf, accf = full.run_chains(k_f, inits, 1, 8, seed=4)
+        assert np.array_equal(accs, accf), (kind, mode, accs, accf)
+        assert np.max(np.abs(ms - mf)) <= (1e-9 if mode == "fp64" else 1e-6), (kind, mode)
         prob.close()
         full.close()
     dist.barrier()
