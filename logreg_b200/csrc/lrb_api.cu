@@ -159,6 +159,7 @@ struct lrb_handle {
   double* mailbox = nullptr;               // [2][kMaxRanks][kMailStride]
   unsigned long long* flags = nullptr;     // [2][kMaxRanks], directly after the mailbox
   unsigned long long* seq = nullptr;
+  int* comm_error = nullptr;
   void* peer_base[kMaxRanks] = {};
   bool peer_open[kMaxRanks] = {};
 
@@ -345,6 +346,7 @@ FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
   f.mailbox_local = h->mailbox;
   f.flags_local = h->flags;
   f.seq = h->seq;
+  f.comm_error = h->comm_error;
   for (int r = 0; r < kMaxRanks; ++r) {
     f.mailbox_peer[r] = nullptr;
     f.flags_peer[r] = nullptr;
@@ -482,6 +484,8 @@ extern "C" int lrb_create(int device, lrb_handle** out) {
   CKC(cudaMemset(h->state, 0, sizeof(SamplerState)));
   CKC(cudaMalloc(&h->seq, sizeof(unsigned long long)));
   CKC(cudaMemset(h->seq, 0, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&h->comm_error, sizeof(int)));
+  CKC(cudaMemset(h->comm_error, 0, sizeof(int)));
   CKC(cudaMallocHost(&h->pinned, (2 * kMaxP + 8) * sizeof(double)));
 #undef CKC
   *out = h;
@@ -498,7 +502,7 @@ extern "C" int lrb_destroy(lrb_handle* h) {
     if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   free_data(h);
   void* bufs[] = {h->d_pscale, h->d_logps, h->partials, h->ticket, h->sums, h->res, h->beta, h->d_init,
-                  h->d_scale, h->state, h->seq, h->d_out, h->d_z, h->d_u, h->mailbox,
+                  h->d_scale, h->state, h->seq, h->comm_error, h->d_out, h->d_z, h->d_u, h->mailbox,
                   h->states_mc, h->sums_mc, h->res_mc, h->beta_mc, h->partials_tc};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -1028,12 +1032,15 @@ int finish_run(lrb_handle* h, double* out, int64_t* accepted) {
   if (out && cnt) CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   std::vector<long long> acc(C, 0);
   std::vector<int> phase(C, -1);
+  int comm_err = 0;
+  CK(h, cudaMemcpyAsync(&comm_err, h->comm_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SamplerState* st = run_states(h);
   CK(h, cudaMemcpy2DAsync(acc.data(), sizeof(long long), &st->accepted, sizeof(SamplerState), sizeof(long long), C,
                           cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpy2DAsync(phase.data(), sizeof(int), &st->phase, sizeof(SamplerState), sizeof(int), C,
                           cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
+  if (comm_err) return fail(h, LRB_E_NCCL, "peer-memory allreduce timed out: a rank of the row-sharded group did not deliver its sums");
   for (int c = 0; c < C; ++c) {
     if (accepted) accepted[c] = acc[c];
     if (phase[c] != PH_PAUSED)

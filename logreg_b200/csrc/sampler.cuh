@@ -59,6 +59,7 @@ struct FinishArgs {
   double* mailbox_peer[kMaxRanks];
   unsigned long long* flags_peer[kMaxRanks];
   unsigned long long* seq;
+  int* comm_error;           // set to 1 if a peer's sums did not arrive within ~4 s (a rank died)
 };
 
 constexpr int kMailStride = kMaxP + 1;  // doubles per (slot, rank) mailbox entry
@@ -299,8 +300,13 @@ __device__ inline void finish_eval(const FinishArgs& f, double* sums, double* sc
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(seq + 1) : "memory");
       const unsigned long long* mine = f.flags_local + (size_t)slot * kMaxRanks + j;
       unsigned long long got;
+      const long long t_start = clock64();
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+        if (got < seq + 1 && clock64() - t_start > 8000000000ll) {   // ~4 s: a peer is gone; do not hang the GPU
+          if (f.comm_error) *f.comm_error = 1;
+          break;
+        }
       } while (got < seq + 1);
     }
     __syncthreads();
