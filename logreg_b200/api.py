@@ -126,6 +126,34 @@ class Problem:
         self._cache_key = None
         return self
 
+    def bind_torch(self, X, y, pscale=None, mode="fp32"):
+        """Bind data that already lives on this GPU as torch tensors (float32/float64 X of shape
+        (n, p) with unit stride along one axis; y float32/float64/uint8). torch is only the owner
+        of the buffers: the library re-lays the data out into its own storage."""
+        import torch
+        if not (X.is_cuda and y.is_cuda and X.dim() == 2):
+            raise ValueError("bind_torch needs 2-D CUDA tensors")
+        n, p = X.shape
+        xd = {torch.float32: N.F32, torch.float64: N.F64}[X.dtype]
+        yd = {torch.float32: N.F32, torch.float64: N.F64, torch.uint8: N.U8}[y.dtype]
+        if X.stride(1) == 1:
+            layout, ld = N.ROW_MAJOR, X.stride(0)
+        elif X.stride(0) == 1:
+            layout, ld = N.COL_MAJOR, X.stride(1)
+        else:
+            X = X.contiguous()
+            layout, ld = N.ROW_MAJOR, p
+        y = y.contiguous()
+        ps = _vec(1.0 if pscale is None else pscale, p, "pscale")
+        torch.cuda.current_stream(X.device).synchronize()
+        self._ck(self._lib.lrb_bind_data(self._h, C.c_void_p(X.data_ptr()), xd, layout, int(ld),
+                                         C.c_void_p(y.data_ptr()), yd, int(n), int(p), N.as_dp(ps),
+                                         _MODES[mode], N.DEVICE))
+        self.n, self.p, self.pscale = int(n), int(p), ps
+        self.n_global = self.n_global or int(n)
+        self._cache_key = None
+        return self
+
     def gen_synthetic(self, n, p, mode="fp32", seed=42, beta_true=None, pscale=None, row_offset=0):
         """On-device synthetic problem. Returns beta_true."""
         if beta_true is None:

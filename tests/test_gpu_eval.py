@@ -213,3 +213,48 @@ def test_full_size_properties():
     assert tot_l == pytest.approx(l_t, rel=1e-11)
     scale = np.max(np.abs(tot_g)) + 1.0
     assert np.max(np.abs((tot_g - bt / prob.pscale ** 2) - g_t)) <= 1e-9 * max(scale, np.sqrt(n))
+
+
+def test_bind_from_device_tensors(lr, synth):
+    """LRB_DEVICE location: data owned by torch on the GPU, every layout / dtype combination."""
+    import torch
+    X32 = synth["X32"]
+    ref = lr.Problem().bind_data(X32, synth["y"], synth["pscale"], mode="fp32")
+    b = synth["B"][1]
+    want = ref.eval(b)
+    Xt = torch.from_numpy(X32).cuda()
+    yt = torch.from_numpy(synth["y"]).cuda()
+    variants = [(Xt, yt), (Xt.t().contiguous().t(), yt), (Xt.double(), yt.double()),
+                (torch.cat([Xt, Xt], dim=1)[:, :32], yt.to(torch.uint8))]
+    for Xv, yv in variants:
+        got = lr.Problem().bind_torch(Xv, yv, synth["pscale"], mode="fp32").eval(b)
+        assert got[0] == want[0] and got[1] == want[1]
+        np.testing.assert_array_equal(got[2], want[2])
+    got64 = lr.Problem().bind_torch(Xt.double(), yt, synth["pscale"], mode="fp64").eval(b)
+    assert got64[0] == pytest.approx(synth["lpost"][1], rel=1e-10)
+
+
+def test_chunked_host_ingest_col_major_equals_row_major(lr):
+    """Host arrays larger than the 256 MB staging buffer stream through in row blocks
+    (cudaMemcpy2D for the reference's column-major layout): 1.2e6 x 64 float64 = 614 MB."""
+    n, p = 1_200_003, 64
+    rs = np.random.RandomState(12)
+    Xc = rs.randn(n, p).astype(np.float32).astype(np.float64)
+    Xc[:, 0] = 1.0
+    bt = rs.randn(p) / 8
+    y = (rs.rand(n) < 1 / (1 + np.exp(-Xc.dot(bt)))).astype(np.float32)
+    a = lr.Problem().bind_data(Xc, y, np.ones(p), mode="fp64")
+    f = lr.Problem().bind_data(np.asfortranarray(Xc), y, np.ones(p), mode="fp64")
+    ra, rf = a.eval(bt), f.eval(bt)
+    assert ra[0] == rf[0]
+    np.testing.assert_array_equal(ra[2], rf[2])
+    assert a.ll(np.zeros(p)) == pytest.approx(-n * np.log(2.0), rel=1e-13)
+    # rows at the block boundaries came through intact
+    for r0 in (0, 524287, 524288, 1048575, 1048576, n - 3):
+        Xo, yo = f.copy_rows(r0, 3)
+        np.testing.assert_array_equal(Xo, Xc[r0:r0 + 3])
+        np.testing.assert_array_equal(yo, y[r0:r0 + 3])
+    from oracle import logreg_oracle as O
+    lp_ref, g_ref = O.Target(Xc, y, np.ones(p)).lpost_glp_chunked(bt)
+    assert ra[0] == pytest.approx(lp_ref, rel=1e-10)
+    assert np.max(np.abs(ra[2] - g_ref)) <= 1e-10 * ungrad_scale(Xc, y, bt, np.ones(p))
