@@ -52,7 +52,7 @@ def step_size(w, n):
     # posterior sd ~ 2.2/sqrt(n) per coefficient (unit-variance covariates): scale steps with it
     sd = 2.2 / np.sqrt(n)
     if w["sampler"] == "hmc":
-        return 1.5 * sd / w["L"]          # trajectory ~ 1.5 sd: acceptance > 0.8
+        return 5.0 * sd / w["L"]          # 0.25 sd per leap-frog step, trajectory ~ 5 sd
     if w["sampler"] == "mala":
         return (0.6 * sd) ** 2            # dt = sd_prop^2
     return (0.3 * sd) ** 2
@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--n", type=int, default=0, help="override total rows (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -419,7 +419,7 @@ def main():
                     "single_call_value": e2e_single, "one_off_ingest": ingest,
                     "note": "K mcmc(x, kernel, thin=1, iters=1) calls, host state in/out each step (each call adds the "
                             "evaluation at its init: L+1 passes per step); single_call_value = one mcmc(iters=K) call"},
-            "gpu_launches": int(launches), "comm": (args.comm if world > 1 else None), "clocks": clk}
+            "gpu_launches": int(launches), "comm": (getattr(prob, "comm_kind", args.comm) if world > 1 else None), "clocks": clk}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

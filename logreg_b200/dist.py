@@ -53,12 +53,31 @@ def _allgather_bytes(buf: bytes) -> bytes:
 
 def init_comm(problem, kind: str = "p2p"):
     """Join `problem` (already created on this rank's GPU) to the row-sharded group
-    of the initialised torch.distributed process group. kind: "nccl" or "p2p"."""
+    of the initialised torch.distributed process group. kind: "nccl", "p2p", or "auto"
+    (the fused peer-memory allreduce if every rank can map its peers, else NCCL)."""
+    import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = problem._lib
     if world == 1:
         return problem
+    if kind == "auto":
+        ok = 1
+        try:
+            mine = C.create_string_buffer(64)
+            N.check(lib.lrb_comm_p2p_export(problem._h, mine), problem._h)
+            allh = _allgather_bytes(mine.raw)
+            N.check(lib.lrb_comm_p2p_connect(problem._h, rank, world, C.create_string_buffer(allh, 64 * world)), problem._h)
+        except Exception:
+            ok = 0
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 1:
+            dist.barrier()
+            problem.world, problem.rank, problem.comm_kind = world, rank, "p2p"
+            return problem
+        kind = "nccl"     # some rank could not map peer memory: everyone falls back together
     if kind == "nccl":
         libnccl = _build.nccl_library().encode()
         uid = C.create_string_buffer(128)
@@ -74,7 +93,7 @@ def init_comm(problem, kind: str = "p2p"):
         dist.barrier()
     else:
         raise ValueError("kind must be 'nccl' or 'p2p'")
-    problem.world, problem.rank = world, rank
+    problem.world, problem.rank, problem.comm_kind = world, rank, kind
     return problem
 
 
