@@ -135,6 +135,13 @@ def cpu_kernel(w, n_full, ns):
 
 
 def time_cpu(w, n_full, steps, warmup, budget_s=None):
+    # use every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently make the reference arm single-threaded
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     ns = min(SAMPLE_ROWS, n_full)
     step, st = cpu_kernel(w, n_full, ns)
     np.random.seed(7)

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
   if (tid == 0) *a.ticket = 0u;  // re-arm for the next launch (stream-ordered)
+  if (a.fuse_finish) prefetch_finish_inputs(a.fin);
 
   // warp w sums the partial vectors of CTAs w, w+8, ... (4 independent accumulators keep
   // 4 L2 loads in flight per lane), lanes stride over the columns; then the 8 warp sums are

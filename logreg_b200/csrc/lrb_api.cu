@@ -147,7 +147,6 @@ struct lrb_handle {
   const double* run_du = nullptr;
   long long run_thin = 0, run_iters = 0;
   lrb_sampler_params run_params{};
-  std::vector<double> run_scale;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int graph_nodes = 0;

@@ -272,6 +272,22 @@ __global__ void sampler_begin_kernel(SamplerState* states, const double* init, c
   }
 }
 
+// Warm L1 with everything finish_eval / sampler_on_eval will read, so those (dependent) loads
+// overlap the reduction of the CTA partials instead of following it.  Call only after the
+// gpu-scope fence that follows the ticket (it invalidates this SM's L1).
+__device__ inline void prefetch_finish_inputs(const FinishArgs& f) {
+  const int j = threadIdx.x;
+  auto pf = [](const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
+  if (j < f.p) {
+    pf(f.beta + j); pf(f.pscale + j); pf(f.log_pscale + j);
+    if (f.state) {
+      const SamplerState* st = f.state;
+      pf(st->x + j); pf(st->gx + j); pf(st->q + j); pf(st->mom + j); pf(st->scale + j); pf(st->sqrt_scale + j);
+    }
+  }
+  if (j == 0 && f.state) pf(f.state);
+}
+
 // ---------------------------------------------------------------- finish
 // sums (shared memory, p+1 doubles): [ll, X'(y-p)] summed over all rows of this
 // rank.  Combines across ranks (fused peer-memory mode), adds the prior
