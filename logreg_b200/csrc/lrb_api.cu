@@ -372,7 +372,7 @@ int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_
   a.fuse_finish = nccl_mode ? 0 : 1;
   EvalFn fn = want_grad ? h->kern.grad : h->kern.nograd;
   const int grid = want_grad ? h->grid : h->grid_nograd;
-  if (h->pdl && !nccl_mode) {
+  if (h->pdl && h->world == 1) {   // measured: helps single-GPU small-n loops, neutral-to-negative with the peer exchange
     // programmatic dependent launch: the grid may start while the previous evaluation's last CTA
     // is still in its reduction / sampler update (see the prologue of eval_kernel)
     cudaLaunchConfig_t cfg{};
