@@ -390,3 +390,32 @@ def test_tensor_core_lockstep_mala_matches_simt_path(lr):
         same = np.all(np.abs(mats[c] - m1) < 5e-3 * sd, axis=1)
         first_bad = len(same) if same.all() else int(np.argmin(same))
         assert first_bad >= 10, (c, first_bad)
+
+
+@pytest.mark.parametrize("kind,thin,iters", [("rwmh", 200, 4000), ("ul", 400, 3000), ("mala", 200, 4000), ("hmc", 10, 3000)])
+def test_pima_posterior_within_mc_error_of_reference_samplers(lr, pima, kind, thin, iters):
+    """BASELINE.json config 1: posterior means / sds on Pima within Monte Carlo error of the
+    REFERENCE samplers. tests/golden/pima_posterior.npz holds mean / sd / ESS of chains produced by
+    the reference's own mcmc + kernels (make_posterior.py); the device chain uses the same tuning
+    constants (fit-numpy.py:81-86, fit-np-ul.py:88, fit-np-mala.py:99, fit-np-hmc.py:108) with the
+    on-device Philox stream. UL is biased by construction -- in the reference too -- so it is
+    compared with the reference's UL, not with the exact posterior."""
+    import os
+    from logreg_b200.workflow import effective_sample_size
+    post = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "pima_posterior.npz")))
+    prob = lr.Problem().bind_data(np.asfortranarray(pima["X"]), pima["y"], pima["pscale"])
+    k = make_kernel(lr, prob, pima, kind)
+    mat, acc = prob.run(k, pima["map"], thin, iters, seed=20260101)
+    m, s, ess = mat.mean(0), mat.std(0, ddof=1), effective_sample_size(mat)
+    rm, rsd, ress = post[kind + "_mean"], post[kind + "_sd"], post[kind + "_ess"]
+    se = np.sqrt(rsd ** 2 / np.maximum(ress, 4.0) + s ** 2 / np.maximum(ess, 4.0))
+    z = np.abs(m - rm) / se
+    assert np.all(z < 4.5), (kind, z)
+    # standard deviations: relative MC error of an sd estimate ~ 1/sqrt(2*ESS) per chain
+    rel = np.abs(s / rsd - 1.0)
+    tol = 4.5 * np.sqrt(0.5 / np.maximum(ress, 4.0) + 0.5 / np.maximum(ess, 4.0)) + 0.05
+    assert np.all(rel < tol), (kind, rel, tol)
+    if kind != "ul":
+        rate = acc / (thin * iters)
+        lo, hi = {"rwmh": (0.02, 0.2), "mala": (0.1, 0.5), "hmc": (0.85, 1.0)}[kind]   # SURVEY appendix B: 0.05 / 0.26 / 0.96
+        assert lo < rate <= hi, (kind, rate)
