@@ -59,6 +59,7 @@ struct EvalTcArgs {
   double* partials;            // [gridDim.x][gridDim.y][P+kTcSub][128]: ll slices, then gll_j
   const SamplerState* states;  // pause check (nullptr for a bare evaluation)
   float* dbg_eta;              // optional: eta of tile 0, [gridDim.y*128][kTcRows]
+  long long* dbg_time;         // optional: clock64 stamps of CTA (0,0), [64 tiles][16 events] (development)
 };
 
 namespace tc {
@@ -241,6 +242,8 @@ __device__ __forceinline__ float tc_link_chunk(uint32_t (&v)[16], uint32_t (&w)[
   return acc;
 }
 
+#define TC_STAMP(i, ev) do { if (a.dbg_time != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 64) a.dbg_time[(i) * 16 + (ev)] = clock64(); } while (0)
+
 template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1)
 eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant__ CUtensorMap xmap_mn,
@@ -324,6 +327,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         const int s = i % NS;
         const int tile = blockIdx.x + i * gridDim.x;
         mbar_wait(bar(X_EMPTY + s), ((i / NS) & 1) ^ 1);
+        TC_STAMP(i, 0);
         mbar_expect_tx(bar(X_FULL + s), 2u * Lay::kXTileBytes + (uint32_t)kTcRows);
         const uint32_t dst = base + s * Lay::kStageBytes;
 #pragma unroll
@@ -345,6 +349,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       const bool first_of_group = (j % kFlush) == 0;
       if (first_of_group && g >= 2) mbar_wait(bar(G_FREE + gb), ((g >> 1) - 1) & 1);
       tc_fence_after();
+      if (lane == 0) TC_STAMP(j, 9);
       const uint32_t xs = base + s * Lay::kStageBytes;
       // MN-major, 128B swizzle with 32-byte atoms: 8 rows (K) of 128 bytes per k-chunk;
       // LBO = stride between 32-column (MN) groups, SBO = stride between 4-row (K) groups
@@ -364,12 +369,14 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         if ((j % kFlush) == kFlush - 1 || j == ntiles_mine - 1) tc_commit(bar(G_FULL + gb));
       }
       __syncwarp();
+      if (lane == 0) TC_STAMP(j, 10);
     };
     for (int i = 0; i < ntiles_mine; ++i) {
       const int s = i % NS, b = i & 1;
       mbar_wait(bar(X_FULL + s), (i / NS) & 1);
       mbar_wait(bar(XL_FULL + s), (i / NS) & 1);
       tc_fence_after();
+      if (lane == 0) TC_STAMP(i, 3);
       const uint32_t xs = base + s * Lay::kStageBytes;
       const uint64_t dk = smem_desc(xs + Lay::kOffXk, 16u, 1024u);
       const uint64_t dlk = smem_desc(xs + Lay::kOffXlk, 16u, 1024u);
@@ -389,6 +396,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
         tc_commit(bar(D1_FULL + b));
       }
       __syncwarp();
+      if (lane == 0) TC_STAMP(i, 4);
       if (i > 0) issue_mma2(i - 1);
     }
     if (ntiles_mine > 0) issue_mma2(ntiles_mine - 1);
@@ -398,6 +406,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
     for (int i = 0; i < ntiles_mine; ++i) {
       const int s = i % NS;
       mbar_wait(bar(X_FULL + s), (i / NS) & 1);
+      if (ct == 0) TC_STAMP(i, 1);
       if (ct < kTcRows)
         reinterpret_cast<float*>(gen + Lay::kOffYf + s * 256)[ct] = (float)(gen + Lay::kOffY + s * 128)[ct];
 #pragma unroll
@@ -415,6 +424,7 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       }
       fence_async_smem();
       mbar_arrive(bar(XL_FULL + s));
+      if (ct == 0) TC_STAMP(i, 2);
     }
   } else if (is_epi) {
     // ===================== epilogue: thread = (chain, 16-row slice of the tile)
@@ -443,10 +453,12 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       const long long row0 = (long long)(blockIdx.x + (long long)i * gridDim.x) * kTcRows + sub * 16;
       mbar_wait(bar(D1_FULL + b), (i >> 1) & 1);
       tc_fence_after();
+      if (tid == 128) TC_STAMP(i, 5);
       const float4* yf = reinterpret_cast<const float4*>(gen + Lay::kOffYf + s * 256 + sub * 64);
       uint32_t v[16], w[16];
       const uint32_t taddr = tmem + lane_addr + Lay::kColD1 + b * kTcRows + sub * 16;
       tmem_ld16(taddr, v);
+      if (tid == 128) TC_STAMP(i, 6);
       if (a.dbg_eta != nullptr && blockIdx.x == 0 && i == 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) a.dbg_eta[(size_t)(cg * kTcChains + ci) * kTcRows + sub * 16 + k] = __uint_as_float(v[k]);
@@ -454,11 +466,13 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       float ll_tile;
       if (row0 + 16 <= a.n) ll_tile = tc_link_chunk<false>(v, w, yf, 16);
       else ll_tile = tc_link_chunk<true>(v, w, yf, (int)max(0ll, a.n - row0));
+      if (tid == 128) TC_STAMP(i, 7);
       tmem_st16(taddr, v);
       tmem_st16(tmem + lane_addr + Lay::kColRl + b * kTcRows + sub * 16, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(R_FULL + b));
+      if (tid == 128) TC_STAMP(i, 8);
       ll_acc += (double)ll_tile;
       if ((i % kFlush) == 0 && i > 0) flush(i / kFlush - 1);   // deferred: the group's MMA2s are long done
     }

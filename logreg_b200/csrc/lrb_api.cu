@@ -176,6 +176,7 @@ struct lrb_handle {
   CUtensorMap xmap_k{}, xmap_mn{};
   double* partials_tc = nullptr; size_t partials_tc_cap = 0;
   float* dbg_eta = nullptr;
+  long long* dbg_time = nullptr;
   int tc_min_chains = 12;   // measured crossover, profiles/r1_many_chain_threshold.txt
   bool pdl = true;
   bool l2_persist = true;
@@ -728,6 +729,7 @@ int enqueue_eval_tc(lrb_handle* h, const double* beta_base, long long beta_strid
   a.y = h->y; a.n = h->n; a.ntiles = ntiles;
   a.beta_base = beta_base; a.beta_stride = beta_stride; a.C = C; a.p = h->p;
   a.partials = h->partials_tc; a.states = states; a.dbg_eta = h->dbg_eta;
+  a.dbg_time = h->dbg_time;
   dim3 grid(gx, groups);
   eval_tc_kernel<64><<<grid, kTcThreads, TcLayout<64>::kDynSmem, h->stream>>>(h->xmap_k, h->xmap_mn, a);
   CK(h, cudaGetLastError());
@@ -843,6 +845,27 @@ extern "C" int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float*
   if (e == cudaSuccess && rc == LRB_OK) e = cudaStreamSynchronize(h->stream);
   cudaFree(h->dbg_eta);
   h->dbg_eta = nullptr;
+  if (getenv("LRB_TC_TIMELINE") && rc == LRB_OK) {
+    // development aid: per-tile clock64 stamps of CTA (0,0) for a second, instrumented launch
+    std::vector<long long> tl(64 * 16, 0);
+    cudaMalloc(&h->dbg_time, tl.size() * sizeof(long long));
+    cudaMemset(h->dbg_time, 0, tl.size() * sizeof(long long));
+    enqueue_eval_tc(h, h->beta_mc, h->p, C, nullptr);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(tl.data(), h->dbg_time, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(h->dbg_time);
+    h->dbg_time = nullptr;
+    const char* names[11] = {"tma_issue", "x_full", "xl_done", "mma1_go", "mma1_issued", "d1_full", "ldtm_done",
+                             "math_done", "r_full", "mma2_go", "mma2_issued"};
+    printf("tile");
+    for (int e = 0; e < 11; ++e) printf(" %11s", names[e]);
+    printf("\n");
+    for (int i = 8; i < 40; ++i) {
+      printf("%4d", i);
+      for (int e = 0; e < 11; ++e) printf(" %11lld", tl[i * 16 + e] ? tl[i * 16 + e] - tl[8 * 16] : -1);
+      printf("\n");
+    }
+  }
   if (rc) return rc;
   if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "debug_tc_eta failed: %s", cudaGetErrorString(e));
   return LRB_OK;
