@@ -409,17 +409,22 @@ eval_tc_kernel(const __grid_constant__ CUtensorMap xmap_k, const __grid_constant
       if (ct == 0) TC_STAMP(i, 1);
       if (ct < kTcRows)
         reinterpret_cast<float*>(gen + Lay::kOffYf + s * 256)[ct] = (float)(gen + Lay::kOffY + s * 128)[ct];
+      // both swizzled copies (the offsets are swizzle-agnostic); 8 independent 16-byte loads in
+      // flight per thread: this conversion sits on the stage's critical path
 #pragma unroll
       for (int set = 0; set < 2; ++set) {
         const float4* src = reinterpret_cast<const float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXm : Lay::kOffXk));
         float4* dst = reinterpret_cast<float4*>(gen + s * Lay::kStageBytes + (set ? Lay::kOffXlm : Lay::kOffXlk));
-#pragma unroll 4
-        for (int k = ct; k < (int)(Lay::kXTileBytes / 16); k += 128) {
-          const float4 x = src[k];
+        constexpr int kPer = (int)(Lay::kXTileBytes / 16) / 128;   // chunks per thread per copy (8 at P = 64)
+        float4 x[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) x[u] = src[ct + u * 128];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
           float4 l;
-          l.x = x.x - trunc_tf32(x.x); l.y = x.y - trunc_tf32(x.y);
-          l.z = x.z - trunc_tf32(x.z); l.w = x.w - trunc_tf32(x.w);
-          dst[k] = l;
+          l.x = x[u].x - trunc_tf32(x[u].x); l.y = x[u].y - trunc_tf32(x[u].y);
+          l.z = x[u].z - trunc_tf32(x[u].z); l.w = x[u].w - trunc_tf32(x[u].w);
+          dst[ct + u * 128] = l;
         }
       }
       fence_async_smem();
