@@ -258,3 +258,40 @@ def test_chunked_host_ingest_col_major_equals_row_major(lr):
     lp_ref, g_ref = O.Target(Xc, y, np.ones(p)).lpost_glp_chunked(bt)
     assert ra[0] == pytest.approx(lp_ref, rel=1e-10)
     assert np.max(np.abs(ra[2] - g_ref)) <= 1e-10 * ungrad_scale(Xc, y, bt, np.ones(p))
+
+
+def test_fp32_mode_against_fp64_mode_at_scale():
+    """Same synthetic rows in both modes (the generator stores float32-representable values either
+    way): at n = 2e7 the FP32-mode result must agree with the FP64-mode result to the FP32-mode
+    tolerance (1e-5) -- and, what a Metropolis test actually needs, to a small ABSOLUTE error in
+    lpost even though |lpost| ~ 1e7."""
+    import logreg_b200 as lr
+    n, p = 20_000_000, 64
+    a, b = lr.Problem(), lr.Problem()
+    bt = a.gen_synthetic(n, p, mode="fp32", seed=42)
+    b.gen_synthetic(n, p, mode="fp64", seed=42, beta_true=bt)
+    Xa, ya = a.copy_rows(n - 1000, 1000)
+    Xb, yb = b.copy_rows(n - 1000, 1000)
+    np.testing.assert_array_equal(Xa, Xb)
+    np.testing.assert_array_equal(ya, yb)
+    rs = np.random.RandomState(5)
+    sd = 2.2 / np.sqrt(n)
+    worst_abs, worst_g = 0.0, 0.0
+    for beta in (bt, bt + 3 * sd * rs.randn(p), bt + 0.05 * rs.randn(p)):
+        lp32, l32, g32 = a.eval(beta)
+        lp64, l64, g64 = b.eval(beta)
+        assert abs(lp32 - lp64) <= 1e-5 * abs(lp64)
+        # un-cancelled gradient magnitude is at least sum_i |r_i| ~ 0.3 n for column 0
+        scale = 0.3 * n
+        assert np.max(np.abs(g32 - g64)) <= 1e-5 * scale
+        worst_abs = max(worst_abs, abs(lp32 - lp64))
+        worst_g = max(worst_g, float(np.max(np.abs(g32 - g64))))
+    # differences of lpost between nearby points (what accept/reject uses) are far more accurate
+    # than the values themselves
+    q0, q1 = bt + sd * rs.randn(p), bt + sd * rs.randn(p)
+    d32 = a.eval(q1)[0] - a.eval(q0)[0]
+    d64 = b.eval(q1)[0] - b.eval(q0)[0]
+    print(f"fp32-vs-fp64 at n=2e7: max |dlpost| = {worst_abs:.3e}, max |dglp| = {worst_g:.3e}, "
+          f"lpost difference error = {abs(d32 - d64):.3e} (difference {d64:.3f})")
+    assert worst_abs < 0.5
+    assert abs(d32 - d64) < 0.05
