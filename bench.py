@@ -424,8 +424,9 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": 2 * p * 8, "d2h_bytes_per_step": p * 8 + 8 + 4,
                     "single_call_value": e2e_single, "one_off_ingest": ingest,
-                    "note": "K mcmc(x, kernel, thin=1, iters=1) calls, host state in/out each step (each call adds the "
-                            "evaluation at its init: L+1 passes per step); single_call_value = one mcmc(iters=K) call"},
+                    "note": "K mcmc(x, kernel, thin=1, iters=1) calls, host state in/out each step (a call that starts "
+                            "where the previous one stopped reuses the cached gradient: L passes per step); "
+                            "single_call_value = one mcmc(iters=K) call"},
             "gpu_launches": int(launches), "comm": (getattr(prob, "comm_kind", args.comm) if world > 1 else None), "clocks": clk}
     print(json.dumps(line))
     if world > 1:

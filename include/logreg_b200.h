@@ -67,6 +67,12 @@ enum lrb_rng {
                          (fit-numpy.py:84,58; fit-np-hmc.py:85,60; UL: no U)         */
 };
 
+/* lrb_sampler_params.flags: `init` is bit-for-bit the state the previous run of the SAME sampler
+ * (MALA or HMC) on this handle ended in, so its cached gradient (and, for HMC, lpost) are reused
+ * instead of re-evaluated. The result is identical to a run without the flag; one pass over X is
+ * saved. Ignored when there is no such paused chain. */
+#define LRB_RUN_REUSE_CACHE 1
+
 typedef struct lrb_handle lrb_handle;
 
 typedef struct lrb_sampler_params {
@@ -77,7 +83,7 @@ typedef struct lrb_sampler_params {
                           fit-numpy.py:84); UL/MALA: `pre`; HMC: `dmm` (mass diagonal) */
   uint64_t seed;       /* Philox key */
   int32_t rng;         /* enum lrb_rng */
-  int32_t reserved;
+  int32_t flags;       /* LRB_RUN_* bits */
   double init_lpost;   /* log-density carried in with `init` for the samplers that thread it
                           (RWMH, MALA: the `ll` argument of kernel(x, ll), fit-numpy.py:54).
                           mcmc() passes -inf, which makes the first proposal always accepted

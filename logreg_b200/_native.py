@@ -19,6 +19,7 @@ HOST, DEVICE = 0, 1
 MODE_FP64, MODE_FP32 = 0, 1
 RWMH, UL, MALA, HMC = 0, 1, 2, 3
 RNG_PHILOX, RNG_REPLAY = 0, 1
+RUN_REUSE_CACHE = 1
 
 
 class LogregB200Error(RuntimeError):
@@ -30,7 +31,7 @@ class LogregB200Error(RuntimeError):
 class SamplerParams(C.Structure):
     _fields_ = [("sampler", C.c_int32), ("l", C.c_int32), ("step", C.c_double),
                 ("scale", C.POINTER(C.c_double)), ("seed", C.c_uint64),
-                ("rng", C.c_int32), ("reserved", C.c_int32), ("init_lpost", C.c_double)]
+                ("rng", C.c_int32), ("flags", C.c_int32), ("init_lpost", C.c_double)]
 
 
 class Info(C.Structure):

@@ -989,10 +989,13 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
       d_init = h->beta_mc;
     }
   }
+  // reuse the cached gradient / lpost of the paused chain when the caller vouches that init is its state
+  const int reuse = (init && (params->flags & LRB_RUN_REUSE_CACHE) && h->chain_live && h->chain_kind == kind &&
+                     h->chain_C == C && (kind == LRB_MALA || kind == LRB_HMC)) ? 1 : 0;
   h->run_C = C;
   sampler_begin_kernel<<<C, kBlock, 0, h->stream>>>(run_states(h), d_init, h->d_scale, kind, params->l, p,
                                                     params->rng, params->step, params->seed,
-                                                    params->init_lpost, steps, thin, dz, du, h->d_out);
+                                                    params->init_lpost, steps, thin, dz, du, h->d_out, reuse);
   CK(h, cudaGetLastError());
   h->kernel_launches++;
   CK(h, cudaStreamSynchronize(h->stream));  // staging buffers are reused by the caller's next call
@@ -1002,7 +1005,7 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   h->run_want_grad = kind != LRB_RWMH;
   h->run_thin = thin;
   h->run_iters = iters;
-  h->pending_init_eval = init != nullptr && (kind == LRB_MALA || kind == LRB_HMC) && steps > 0;
+  h->pending_init_eval = init != nullptr && !reuse && (kind == LRB_MALA || kind == LRB_HMC) && steps > 0;
   h->run_dz = dz;
   h->run_du = du;
   h->run_consumed = false;
@@ -1024,7 +1027,7 @@ int launch_run(lrb_handle* h) {
     sampler_begin_kernel<<<h->run_C, kBlock, 0, h->stream>>>(run_states(h), nullptr, h->d_scale, h->run_kind,
                                                              h->run_params.l, h->p, h->run_params.rng,
                                                              h->run_params.step, h->run_params.seed, 0.0, steps,
-                                                             h->run_thin, h->run_dz, h->run_du, h->d_out);
+                                                             h->run_thin, h->run_dz, h->run_du, h->d_out, 0);
     CK(h, cudaGetLastError());
     h->kernel_launches++;
   }

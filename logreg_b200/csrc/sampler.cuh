@@ -232,7 +232,7 @@ __device__ inline void sampler_on_eval(SamplerState* st, double lp, double g, do
 __global__ void sampler_begin_kernel(SamplerState* states, const double* init, const double* scale,
                                      int kind, int l, int p, int rng, double step, uint64_t seed,
                                      double init_lpost, long long steps, long long thin, const double* z,
-                                     const double* u, double* out) {
+                                     const double* u, double* out, int reuse_cache) {
   __shared__ double scratch[kWarps];
   const int j = threadIdx.x;
   const long long c = blockIdx.x;
@@ -247,7 +247,10 @@ __global__ void sampler_begin_kernel(SamplerState* states, const double* init, c
     st->kind = kind; st->l = l; st->p = p; st->rng = rng;
     st->step = step; st->sqrt_step = sqrt(step);
     st->seed = seed + (uint64_t)c * 0x9E3779B97F4A7C15ull;
-    if (init) { st->t = 0; st->accepted = 0; st->lp_x = init_lpost; st->k0 = 0.0; }
+    if (init) {
+      st->t = 0; st->accepted = 0; st->k0 = 0.0;
+      if (!(reuse_cache && kind == S_HMC)) st->lp_x = init_lpost;   // HMC keeps the cached lpost(x)
+    }
     st->t_run0 = st->t;
     st->t_replay0 = st->t;
     st->t_end = st->t + steps;
@@ -261,7 +264,7 @@ __global__ void sampler_begin_kernel(SamplerState* states, const double* init, c
   if (steps <= 0) { if (j == 0) st->phase = PH_PAUSED; return; }
   // Which samplers need the gradient (and lpost) of the starting state first?
   // A continued MALA/HMC chain still has them cached.
-  const bool need_init = init != nullptr && (kind == S_MALA || kind == S_HMC);
+  const bool need_init = init != nullptr && !reuse_cache && (kind == S_MALA || kind == S_HMC);
   if (need_init) {
     if (j < p) st->beta_in[j] = st->x[j];
     if (j == 0) st->phase = PH_INIT;

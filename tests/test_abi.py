@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     from logreg_b200 import _native as N
     # lrb_sampler_params: int32 int32 double ptr uint64 int32 int32 double = 48 bytes on LP64
     assert C.sizeof(N.SamplerParams) == 48
-    assert N.SamplerParams.scale.offset == 16 and N.SamplerParams.init_lpost.offset == 40
+    assert N.SamplerParams.scale.offset == 16 and N.SamplerParams.flags.offset == 36 and N.SamplerParams.init_lpost.offset == 40
     # lrb_info: int64 + 8*int32 + 3*int64 = 64 bytes
     assert C.sizeof(N.Info) == 64 and N.Info.bytes_per_eval.offset == 40
 

@@ -419,3 +419,28 @@ def test_pima_posterior_within_mc_error_of_reference_samplers(lr, pima, kind, th
         rate = acc / (thin * iters)
         lo, hi = {"rwmh": (0.02, 0.2), "mala": (0.1, 0.5), "hmc": (0.85, 1.0)}[kind]   # 0.05 / 0.26 / 0.96
         assert lo < rate <= hi, (kind, rate)
+
+
+@pytest.mark.parametrize("kind,epi", [("hmc_l7", 7), ("mala", 1)])
+def test_stepwise_calls_reuse_the_cached_state(lr, pima, kind, epi):
+    """mcmc / kernel calls that start exactly where the previous call stopped skip the evaluation
+    at init (LRB_RUN_REUSE_CACHE): same chain as a cold start from that state, one pass less."""
+    X = np.asfortranarray(pima["X"])
+    a = lr.Problem().bind_data(X, pima["y"], pima["pscale"])
+    ka = make_kernel(lr, a, pima, kind)
+    m1, _ = a.run(ka, pima["chain_init"], 1, 5, seed=1)
+    e0 = a.info()["eval_launches"]
+    m2, acc2 = a.run(ka, m1[-1], 1, 6, seed=2)
+    warm = a.info()["eval_launches"] - e0
+    b = lr.Problem().bind_data(X, pima["y"], pima["pscale"])
+    kb = make_kernel(lr, b, pima, kind)
+    e0 = b.info()["eval_launches"]
+    m3, acc3 = b.run(kb, m1[-1], 1, 6, seed=2)
+    cold = b.info()["eval_launches"] - e0
+    np.testing.assert_array_equal(m2, m3)
+    assert acc2 == acc3
+    assert cold == 6 * epi + 1 and warm == 6 * epi
+    # a different starting point must NOT reuse anything
+    e0 = a.info()["eval_launches"]
+    a.run(ka, m1[-1] + 1e-9, 1, 2, seed=3)
+    assert a.info()["eval_launches"] - e0 == 2 * epi + 1
