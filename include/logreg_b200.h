@@ -155,9 +155,11 @@ int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
 int lrb_eval_device(lrb_handle* h, const double* d_beta, double* d_out, int want_grad);
 
 /* Diagnostic for the tensor-core many-chain kernel: runs it on C coefficient vectors and
- * returns eta = x.beta of the FIRST 128-row tile, eta_out[ceil(C/128)*128][128] (chain-major),
- * as the tensor cores produced it (3xTF32).  Test instrumentation; not part of the drop-in path. */
+ * returns eta = x.beta of the FIRST row tile, eta_out[ceil(C/128)*128][lrb_tc_tile_rows()]
+ * (chain-major), as the tensor cores produced it (3xTF32).  Test instrumentation; not part of the
+ * drop-in path. */
 int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float* eta_out);
+int lrb_tc_tile_rows(void);
 
 /* lprior alone (fit-np-ul.py:33-34; no pass over X). beta: C x p host; out: C. */
 int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "lrb_eval_device": (_i, [_vp, _vp, _vp, _i]),
     "lrb_lprior": (_i, [_vp, _dp, _i, _dp]),
     "lrb_debug_tc_eta": (_i, [_vp, _dp, _i, C.POINTER(C.c_float)]),
+    "lrb_tc_tile_rows": (_i, []),
     "lrb_run": (_i, [_vp, C.POINTER(SamplerParams), _dp, _i, _i64, _i64, _dp, _dp, _dp, C.POINTER(_i64)]),
     "lrb_run_begin": (_i, [_vp, C.POINTER(SamplerParams), _dp, _i64, _i64, _dp, _dp]),
     "lrb_run_launch": (_i, [_vp]),

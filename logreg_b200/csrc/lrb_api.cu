@@ -426,7 +426,7 @@ int alloc_data(lrb_handle* h, long long n, int p, int mode) {
   h->n = n; h->p = p; h->P = pad_p(p); h->mode = mode;
   const size_t es = mode == LRB_MODE_FP32 ? 4 : 8;
   CK(h, cudaMalloc(&h->X, (size_t)n * h->P * es));
-  const size_t ybytes = ((size_t)n + 127) / 128 * 128;   // the tensor-core path copies y in 128-byte tiles
+  const size_t ybytes = ((size_t)n + 127) / 128 * 128 + 128;   // the tensor-core path copies y in whole row tiles
   CK(h, cudaMalloc(&h->y, ybytes));
   CK(h, cudaMemset(h->y, 0, ybytes));
   return LRB_OK;
@@ -824,6 +824,8 @@ extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
   }
   return LRB_OK;
 }
+
+extern "C" int lrb_tc_tile_rows(void) { return kTcRows; }
 
 extern "C" int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float* eta_out) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");

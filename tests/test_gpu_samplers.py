@@ -362,13 +362,14 @@ def test_tensor_core_many_chain_eval_against_oracle(lr, n, C):
 
 
 def test_tensor_core_eta_tile(lr):
-    """The contraction itself: eta of the first 64-row tile as the tensor cores produce it."""
+    """The contraction itself: eta of the first row tile as the tensor cores produce it."""
     import ctypes as C
     from logreg_b200 import _native as N
     prob, bt = _tc_problem(lr, 4096)
-    X, y = prob.copy_rows(0, 64)
+    rows = prob._lib.lrb_tc_tile_rows()
+    X, y = prob.copy_rows(0, rows)
     B = bt + 0.1 * np.random.RandomState(1).randn(256, 64)
-    eta = np.zeros((256, 64), dtype=np.float32)
+    eta = np.zeros((256, rows), dtype=np.float32)
     prob._ck(prob._lib.lrb_debug_tc_eta(prob._h, N.as_dp(np.ascontiguousarray(B)), 256,
                                         eta.ctypes.data_as(C.POINTER(C.c_float))))
     ref = (X @ B.T).T

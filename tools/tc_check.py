@@ -14,7 +14,7 @@ rs = np.random.RandomState(1)
 B = bt + 0.1 * rs.randn(Cn, p)
 X, y = prob.copy_rows(0, min(n, 4096))
 groups = (Cn + 127) // 128
-TR = 64
+TR = prob._lib.lrb_tc_tile_rows()
 eta = np.zeros((groups * 128, TR), dtype=np.float32)
 prob._ck(prob._lib.lrb_debug_tc_eta(prob._h, N.as_dp(np.ascontiguousarray(B)), Cn, eta.ctypes.data_as(C.POINTER(C.c_float))))
 ref = (X[:TR] @ B.T).T            # [chain][row]
