@@ -342,7 +342,7 @@ FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
   f.p = h->p;
   f.world = h->world;
   f.rank = h->rank;
-  f.p2p = (h->comm == 2) ? 1 : 0;
+  f.p2p = (h->comm == 2) ? (getenv("LRB_P2P_FENCE") ? 3 : 1) : 0;
   f.mailbox_local = h->mailbox;
   f.flags_local = h->flags;
   f.seq = h->seq;

@@ -312,7 +312,10 @@ __device__ inline void finish_eval(const FinishArgs& f, double* sums, double* sc
       double* dst = f.mailbox_peer[r] + ((size_t)slot * kMaxRanks + f.rank) * kMailStride;
       for (int c = j; c <= p; c += kBlock) dst[c] = sums[c];
     }
-    __threadfence_system();
+    // No system fence per thread: the CTA barrier orders every thread's remote stores before the
+    // st.release.sys of the flag (release is cumulative over what happens-before it), which is
+    // the single system-scope fence of the exchange.
+    if (f.p2p & 2) __threadfence_system();   // A/B knob (LRB_P2P_FENCE=1): the conservative variant
     __syncthreads();
     if (j < f.world && j != f.rank) {
       unsigned long long* fl = f.flags_peer[j] + (size_t)slot * kMaxRanks + f.rank;
