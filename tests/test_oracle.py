@@ -161,3 +161,43 @@ def test_against_live_reference(pima):
     rng = O.ReplayRNG(Z, U)
     mine = O.mcmc_plain(pima["map"], O.hmc_kernel(t.lpost, t.glp, eps=1e-3, l=10, dmm=1 / pima["pre"], rng=rng), 2, 15)
     np.testing.assert_allclose(mine, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_gradient_is_the_derivative_of_lpost(pima, synth):
+    """glp (fit-np-ul.py:45-48) is hand-coded in the reference; check it against central finite
+    differences of lpost (fit-numpy.py:43-44) -- the check the reference does by eye
+    (fit-np-ul.py:50-51,57)."""
+    for X, y, ps, b in ((pima["X"], pima["y"], pima["pscale"], pima["B"][1]),
+                        (synth["X32"].astype(np.float64), synth["y"], synth["pscale"], synth["B"][2])):
+        t = O.Target(X, y, ps)
+        g = t.glp(b)
+        scale = np.abs(X).T.dot(np.ones(len(y))) + 1.0
+        for j in range(len(b)):
+            h = 1e-5 / np.sqrt(scale[j])
+            e = np.zeros(len(b)); e[j] = h
+            fd = (t.lpost(b + e) - t.lpost(b - e)) / (2 * h)
+            assert abs(fd - g[j]) <= 1e-4 * scale[j] * 1e-2 + 1e-6 * abs(g[j]), (j, fd, g[j])
+
+
+def test_oracle_row_additivity_hypothesis(synth):
+    """ll and X'(y-p) are row sums (the property the row-sharded GPU path relies on)."""
+    from hypothesis import given, settings, strategies as st
+    X = synth["X32"].astype(np.float64)
+    t = O.Target(X, synth["y"], synth["pscale"])
+    b = synth["B"][1]
+    full_ll, full_g = t.ll_gll_rows(b, 0, t.n)
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=t.n - 1), min_size=1, max_size=6, unique=True))
+    def check(cuts):
+        edges = [0] + sorted(cuts) + [t.n]
+        ll = 0.0
+        g = np.zeros(t.p)
+        for lo, hi in zip(edges, edges[1:]):
+            a, c = t.ll_gll_rows(b, lo, hi)
+            ll += a
+            g += c
+        assert ll == pytest.approx(full_ll, rel=1e-12)
+        np.testing.assert_allclose(g, full_g, rtol=1e-9, atol=1e-9)
+
+    check()
