@@ -66,3 +66,31 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower().replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The ABI header compiles as strict C99 and the demo links against the library (no run:
+    running needs a GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from logreg_b200 import _native as N
+    N.load()
+    libdir = os.path.dirname(N.library_path())
+    exe = tmp_path / "c_abi_demo"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", str(exe), "-L", libdir, "-llogreg_b200",
+           f"-Wl,-rpath,{libdir}", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    # without a GPU the demo must fail loudly through the error convention, not crash
+    try:
+        have_gpu = N.device_count() > 0
+    except Exception:
+        have_gpu = False
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    if have_gpu:
+        assert run.returncode == 0 and "lpost" in run.stdout, run.stderr
+    else:
+        assert run.returncode == 1 and "no CUDA device" in run.stderr
