@@ -38,7 +38,7 @@ int main(void) {
   CHECK(lrb_eval(h, beta, 1, 1, &lpost, &ll, glp));
   printf("lpost %.10f ll %.10f glp[0] %.10f\n", lpost, ll, glp[0]);
   sp.sampler = LRB_HMC; sp.l = 10; sp.step = 0.02; sp.scale = scale; sp.seed = 7; sp.rng = LRB_RNG_PHILOX;
-  sp.flags = 0; sp.init_lpost = -INFINITY;
+  sp.flags = 0; sp.init_lpost = -INFINITY; sp.t0 = 0;
   CHECK(lrb_run(h, &sp, init, 1, 2, 50, NULL, NULL, out, &accepted));
   printf("HMC: 50 thinned samples, accepted %lld of 100, last state %.4f %.4f %.4f %.4f\n", (long long)accepted,
          out[49 * P], out[49 * P + 1], out[49 * P + 2], out[49 * P + 3]);

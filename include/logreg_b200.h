@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LRB_ABI_VERSION 1
+#define LRB_ABI_VERSION 2
 
 enum lrb_status {
   LRB_OK = 0,
@@ -62,9 +62,15 @@ enum lrb_sampler {
 
 enum lrb_rng {
   LRB_RNG_PHILOX = 0, /* on-device Philox4x32-10, counter = (iteration, coordinate) */
-  LRB_RNG_REPLAY = 1  /* host-supplied N(0,1) rows Z and uniforms U, consumed in the
+  LRB_RNG_REPLAY = 1, /* host-supplied N(0,1) rows Z and uniforms U, consumed in the
                          reference's order: randn(p) then rand() per kernel call
                          (fit-numpy.py:84,58; fit-np-hmc.py:85,60; UL: no U)         */
+  LRB_RNG_KEYED = 2   /* JAX-style split keys (Python/fit-jax2.py:98-116): `seed` is the root key;
+                         kernel application t of the run uses
+                         split(split(root, iters)[t / thin], thin)[t % thin], split once more
+                         inside the kernel exactly as the reference kernels do (mhKernel
+                         fit-jax2.py:90, hmcKernel fit-jax-hmc.py:126-129, ulKernel
+                         fit-jax-ul.py:86-88); split(k, n)[i] = lrb_key_child(k, i)           */
 };
 
 /* lrb_sampler_params.flags: `init` is bit-for-bit the state the previous run of the SAME sampler
@@ -72,6 +78,18 @@ enum lrb_rng {
  * instead of re-evaluated. The result is identical to a run without the flag; one pass over X is
  * saved. Ignored when there is no such paused chain. */
 #define LRB_RUN_REUSE_CACHE 1
+/* Start the chain's kernel-application counter (the Philox counter of LRB_RNG_PHILOX) at
+ * params->t0 instead of 0: a chain checkpointed with lrb_chain_state after `steps` applications
+ * resumes in a NEW process / handle with init = x, init_lpost = lpost, t0 = steps and the same seed
+ * and continues the same random stream.  Ignored when init is NULL. */
+#define LRB_RUN_SET_T0 2
+/* Accumulate running mean and cross-moments of the thinned states on the device (Welford), per
+ * chain; read them with lrb_run_moments.  They restart with a new chain (init != NULL) and keep
+ * accumulating over continued runs (Dex/djwutils.dx:97-103 meanAndCovariance, analyse.R:16). */
+#define LRB_RUN_MOMENTS 4
+/* Do not store the thinned states at all (use with LRB_RUN_MOMENTS for many chains): lrb_run's
+ * `out` is ignored and nothing but the moments ever leaves the device. */
+#define LRB_RUN_NO_SAMPLES 8
 
 typedef struct lrb_handle lrb_handle;
 
@@ -88,6 +106,7 @@ typedef struct lrb_sampler_params {
                           (RWMH, MALA: the `ll` argument of kernel(x, ll), fit-numpy.py:54).
                           mcmc() passes -inf, which makes the first proposal always accepted
                           (fit-numpy.py:66).  Ignored when init is NULL, by UL and by HMC. */
+  int64_t t0;          /* with LRB_RUN_SET_T0: kernel applications already done by the resumed chain */
 } lrb_sampler_params;
 
 typedef struct lrb_info {
@@ -116,6 +135,25 @@ const char* lrb_last_error(const lrb_handle* h);
  * handle's stream. */
 int lrb_set_stream(lrb_handle* h, void* cuda_stream);
 int lrb_synchronize(lrb_handle* h);
+
+/* Per-handle options.
+ *   DETERMINISTIC  0 (default): single-chain evaluations run in "drive mode" -- a persistent
+ *                  cooperative kernel with dynamic row-batch scheduling and atomic (timing-ordered)
+ *                  accumulation of the CTA sums; results are reproducible to rounding (~1e-15
+ *                  relative), not bit for bit.  1: the static kernel, one launch per evaluation,
+ *                  CTA sums added in a fixed order => bit-identical results for a fixed shape.
+ *   TC_MIN_CHAINS  chain count from which the tensor-core many-chain kernel is used (default 12).
+ *   P2P_TIMEOUT_MS bound of every in-kernel wait for a peer rank / another CTA (default 60000).
+ *   PDL            programmatic dependent launch between evaluations of the static kernel.
+ *   L2_PERSIST     pin X in the persisting part of L2 when it is at most 3x the L2 size. */
+enum lrb_option {
+  LRB_OPT_DETERMINISTIC = 1,
+  LRB_OPT_TC_MIN_CHAINS = 2,
+  LRB_OPT_P2P_TIMEOUT_MS = 3,
+  LRB_OPT_PDL = 4,
+  LRB_OPT_L2_PERSIST = 5
+};
+int lrb_set_option(lrb_handle* h, int option, int64_t value);
 int lrb_get_info(const lrb_handle* h, lrb_info* info);
 
 /* ---- data: the script globals X, y, pscale --------------------------------
@@ -161,6 +199,13 @@ int lrb_eval_device(lrb_handle* h, const double* d_beta, double* d_out, int want
 int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float* eta_out);
 int lrb_tc_tile_rows(void);
 
+/* Development instrumentation of the fused streaming kernel: when enabled every CTA records
+ * %globaltimer (ns) at entry, after the grid dependency, at the end of streaming and after its
+ * ticket; the last CTA adds the end of its reduction and of the finish/sampler step.
+ * lrb_debug_timeline_read returns [grid][4] + [8] stamps of the latest evaluation. */
+int lrb_debug_timeline(lrb_handle* h, int enable);
+int lrb_debug_timeline_read(lrb_handle* h, int64_t* out, int64_t cap, int64_t* grid);
+
 /* lprior alone (fit-np-ul.py:33-34; no pass over X). beta: C x p host; out: C. */
 int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out);
 
@@ -190,6 +235,16 @@ int lrb_run_finish(lrb_handle* h, double* out, int64_t* accepted);
 int lrb_chain_state(lrb_handle* h, double* x, double* lpost, int64_t* steps);
 /* fused evaluations one lrb_run_launch enqueues (e.g. thin*iters*l for HMC) */
 int lrb_run_evals_per_launch(const lrb_handle* h, int64_t* evals);
+
+/* Running moments of the thinned states of the latest LRB_RUN_MOMENTS run.
+ * pooled == 0: count[C], mean[C x p], cov[C x p x p] per chain (C = chains of that run);
+ * pooled != 0: all chains combined into count[1], mean[p], cov[p x p].
+ * cov = sum (x - mean)(x - mean)' / (count - 1) (Dex/djwutils.dx:100-102); cov may be NULL. */
+int lrb_run_moments(lrb_handle* h, int pooled, int64_t* count, double* mean, double* cov);
+
+/* split(key, n)[i] of the keyed front-end: words (x, y) of Philox4x32-10 at counter
+ * (i_lo, i_hi, 0, 4) under `key`.  Pure host arithmetic (no GPU needed). */
+uint64_t lrb_key_child(uint64_t key, uint64_t i);
 
 /* Dump the device RNG stream: z_out[count x p] and u_out[count] for iterations
  * t0 .. t0+count-1 under `seed` (what LRB_RNG_PHILOX feeds the samplers). */

@@ -18,8 +18,9 @@ ROW_MAJOR, COL_MAJOR = 0, 1
 HOST, DEVICE = 0, 1
 MODE_FP64, MODE_FP32 = 0, 1
 RWMH, UL, MALA, HMC = 0, 1, 2, 3
-RNG_PHILOX, RNG_REPLAY = 0, 1
-RUN_REUSE_CACHE = 1
+RNG_PHILOX, RNG_REPLAY, RNG_KEYED = 0, 1, 2
+RUN_REUSE_CACHE, RUN_SET_T0, RUN_MOMENTS, RUN_NO_SAMPLES = 1, 2, 4, 8
+OPT_DETERMINISTIC, OPT_TC_MIN_CHAINS, OPT_P2P_TIMEOUT_MS, OPT_PDL, OPT_L2_PERSIST = 1, 2, 3, 4, 5
 
 
 class LogregB200Error(RuntimeError):
@@ -31,7 +32,7 @@ class LogregB200Error(RuntimeError):
 class SamplerParams(C.Structure):
     _fields_ = [("sampler", C.c_int32), ("l", C.c_int32), ("step", C.c_double),
                 ("scale", C.POINTER(C.c_double)), ("seed", C.c_uint64),
-                ("rng", C.c_int32), ("flags", C.c_int32), ("init_lpost", C.c_double)]
+                ("rng", C.c_int32), ("flags", C.c_int32), ("init_lpost", C.c_double), ("t0", C.c_int64)]
 
 
 class Info(C.Structure):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "lrb_last_error": (C.c_char_p, [_vp]),
     "lrb_set_stream": (_i, [_vp, _vp]),
     "lrb_synchronize": (_i, [_vp]),
+    "lrb_set_option": (_i, [_vp, _i, _i64]),
     "lrb_get_info": (_i, [_vp, C.POINTER(Info)]),
     "lrb_bind_data": (_i, [_vp, _vp, _i, _i, _i64, _vp, _i, _i64, _i, _dp, _i, _i]),
     "lrb_gen_synthetic": (_i, [_vp, _i64, _i, _i, _u64, _dp, _dp, _i64]),
@@ -62,12 +64,16 @@ SIGNATURES = {
     "lrb_lprior": (_i, [_vp, _dp, _i, _dp]),
     "lrb_debug_tc_eta": (_i, [_vp, _dp, _i, C.POINTER(C.c_float)]),
     "lrb_tc_tile_rows": (_i, []),
+    "lrb_debug_timeline": (_i, [_vp, _i]),
+    "lrb_debug_timeline_read": (_i, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
     "lrb_run": (_i, [_vp, C.POINTER(SamplerParams), _dp, _i, _i64, _i64, _dp, _dp, _dp, C.POINTER(_i64)]),
     "lrb_run_begin": (_i, [_vp, C.POINTER(SamplerParams), _dp, _i64, _i64, _dp, _dp]),
     "lrb_run_launch": (_i, [_vp]),
     "lrb_run_finish": (_i, [_vp, _dp, C.POINTER(_i64)]),
     "lrb_chain_state": (_i, [_vp, _dp, _dp, C.POINTER(_i64)]),
     "lrb_run_evals_per_launch": (_i, [_vp, C.POINTER(_i64)]),
+    "lrb_run_moments": (_i, [_vp, _i, C.POINTER(_i64), _dp, _dp]),
+    "lrb_key_child": (_u64, [_u64, _u64]),
     "lrb_rng_dump": (_i, [_vp, _u64, _i64, _i64, _i, _dp, _dp]),
     "lrb_nccl_unique_id": (_i, [_vp, C.c_char_p]),
     "lrb_comm_init_nccl": (_i, [_vp, _i, _i, _vp, C.c_char_p]),

@@ -44,11 +44,13 @@ def _vec(v, p, name):
 class Problem:
     """Owns one library handle: the data (the scripts' globals X, y, pscale) on one GPU."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, deterministic: bool = False):
         self._lib = N.load()
         h = C.c_void_p()
         N.check(self._lib.lrb_create(int(device), C.byref(h)))
         self._h = h
+        if deterministic:
+            self.set_option(N.OPT_DETERMINISTIC, 1)
         self.device = int(device)
         self.n = 0
         self.p = 0
@@ -77,6 +79,11 @@ class Problem:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._lib.lrb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_option(self, option: int, value: int):
+        """lrb_set_option: N.OPT_DETERMINISTIC (fixed-order static kernel: bit-identical results),
+        N.OPT_TC_MIN_CHAINS, N.OPT_P2P_TIMEOUT_MS, N.OPT_PDL, N.OPT_L2_PERSIST."""
+        self._ck(self._lib.lrb_set_option(self._h, int(option), int(value)))
 
     def synchronize(self):
         self._ck(self._lib.lrb_synchronize(self._h))
@@ -227,16 +234,24 @@ class Problem:
         return self.eval(beta, want_grad=True)[2].copy()
 
     # ------------------------------------------------------------ sampler runs
-    def _params(self, k, seed, rng, init_lpost, flags=0):
+    def _params(self, k, seed, rng, init_lpost, flags=0, t0=0):
         sp = N.SamplerParams()
         sp.sampler, sp.l, sp.step = k.sampler, int(k.l), float(k.step)
         sp.scale = N.as_dp(k.scale)
-        sp.seed, sp.rng, sp.flags, sp.init_lpost = int(seed), rng, int(flags), float(init_lpost)
+        sp.seed, sp.rng, sp.flags, sp.init_lpost = int(seed) & (2 ** 64 - 1), rng, int(flags), float(init_lpost)
+        sp.t0 = int(t0)
         return sp
 
-    def run(self, kernel, init, thin, iters, Z=None, U=None, seed=0, init_lpost=-np.inf):
-        """One lrb_run call. init=None continues the paused chain. Returns (mat, accepted)."""
-        rng = N.RNG_REPLAY if Z is not None else N.RNG_PHILOX
+    def run(self, kernel, init, thin, iters, Z=None, U=None, seed=0, init_lpost=-np.inf, t0=None,
+            moments=False, keep_samples=True, keyed=False):
+        """One lrb_run call. init=None continues the paused chain. Returns (mat, accepted).
+
+        t0: resume a checkpointed chain (x, lpost, steps = chain_state()) in a new handle: pass
+            init=x, init_lpost=lpost, t0=steps and the same seed -- the Philox stream continues.
+        moments: accumulate running mean / cross-moments of the thinned states on the device
+            (read with .moments()); keep_samples=False then returns mat=None and copies nothing.
+        keyed: `seed` is a JAX-style root key (logreg_b200.jaxlike); draws follow its split tree."""
+        rng = N.RNG_REPLAY if Z is not None else (N.RNG_KEYED if keyed else N.RNG_PHILOX)
         ini = None if init is None else self._beta(init)
         # init is exactly where the last run of this sampler stopped: its cached gradient / lpost
         # are still valid, so the evaluation at init is skipped (same result, one pass less)
@@ -244,8 +259,16 @@ class Problem:
         if (ini is not None and self._last_x is not None and self._last_sampler == kernel.sampler
                 and kernel.sampler in (N.MALA, N.HMC) and ini.tobytes() == self._last_x):
             flags = N.RUN_REUSE_CACHE
-        sp = self._params(kernel, seed, rng, init_lpost, flags)
-        out = np.empty((int(iters), self.p))
+        if t0 is not None:
+            flags |= N.RUN_SET_T0
+        if moments:
+            flags |= N.RUN_MOMENTS
+        if not keep_samples:
+            flags |= N.RUN_NO_SAMPLES
+        sp = self._params(kernel, seed, rng, init_lpost, flags, t0 or 0)
+        if moments:
+            self._moment_chains = 1
+        out = np.empty((int(iters), self.p)) if keep_samples else None
         acc = C.c_int64(0)
         if Z is not None:
             Z = np.ascontiguousarray(Z, dtype=np.float64)
@@ -256,15 +279,31 @@ class Problem:
         self._ck(self._lib.lrb_run(
             self._h, C.byref(sp), None if ini is None else N.as_dp(ini), 1, int(thin), int(iters),
             None if Z is None else N.as_dp(Z), None if U is None else N.as_dp(U),
-            N.as_dp(out), C.byref(acc)))
+            None if out is None else N.as_dp(out), C.byref(acc)))
         self._cache_key = None
-        if int(iters) > 0:
+        if int(iters) > 0 and out is not None:
             self._last_x, self._last_sampler = out[-1].tobytes(), kernel.sampler
-        elif ini is not None:
+        elif ini is not None or out is None:
             self._last_x = None
         return out, acc.value
 
-    def run_chains(self, kernel, inits, thin, iters, Z=None, U=None, seed=0, init_lpost=-np.inf):
+    def moments(self, pooled=False, cov=True):
+        """Device-side running moments of the latest run(s) with moments=True
+        (Dex/djwutils.dx:97-103 meanAndCovariance; what analyse.R's mcmcSummary starts from).
+        Returns (count, mean, cov): per chain (C,), (C, p), (C, p, p), or pooled over the chains
+        int, (p,), (p, p). cov uses the n-1 denominator."""
+        c = 1 if pooled else max(1, getattr(self, "_moment_chains", 1))
+        cnt = np.zeros(c, dtype=np.int64)
+        mean = np.empty((c, self.p))
+        cv = np.empty((c, self.p, self.p)) if cov else None
+        self._ck(self._lib.lrb_run_moments(self._h, 1 if pooled else 0, cnt.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           N.as_dp(mean), None if cv is None else N.as_dp(cv)))
+        if pooled or getattr(self, "_moment_chains", 1) == 1:
+            return int(cnt[0]), mean[0], (None if cv is None else cv[0])
+        return cnt, mean, cv
+
+    def run_chains(self, kernel, inits, thin, iters, Z=None, U=None, seed=0, init_lpost=-np.inf,
+                   moments=False, keep_samples=True):
         """C chains in lock-step on the device (lrb_run with C > 1): inits (C, p) -> samples
         (C, iters, p) and accepted counts (C,). Chain c uses Philox key seed + c*0x9E3779B97F4A7C15
         (mod 2^64), or rows of Z (C, thin*iters, p) / U (C, thin*iters) in replay mode."""
@@ -273,9 +312,12 @@ class Problem:
             raise ValueError(f"inits must have shape (C, {self.p})")
         c = inits.shape[0]
         rng = N.RNG_REPLAY if Z is not None else N.RNG_PHILOX
-        sp = self._params(kernel, seed, rng, init_lpost)
-        out = np.empty((c, int(iters), self.p))
+        flags = (N.RUN_MOMENTS if moments else 0) | (0 if keep_samples else N.RUN_NO_SAMPLES)
+        sp = self._params(kernel, seed, rng, init_lpost, flags)
+        out = np.empty((c, int(iters), self.p)) if keep_samples else None
         acc = np.zeros(c, dtype=np.int64)
+        if moments:
+            self._moment_chains = c
         if Z is not None:
             Z = np.ascontiguousarray(Z, dtype=np.float64)
             if Z.shape != (c, thin * iters, self.p):
@@ -285,7 +327,7 @@ class Problem:
         self._ck(self._lib.lrb_run(
             self._h, C.byref(sp), N.as_dp(inits), c, int(thin), int(iters),
             None if Z is None else N.as_dp(Z), None if U is None else N.as_dp(U),
-            N.as_dp(out), acc.ctypes.data_as(C.POINTER(C.c_int64))))
+            None if out is None else N.as_dp(out), acc.ctypes.data_as(C.POINTER(C.c_int64))))
         self._cache_key = None
         self._last_x = None
         return out, acc
@@ -297,9 +339,15 @@ class Problem:
         return x, lp.value, t.value
 
     def rng_dump(self, seed, t0, count):
-        z = np.empty((count, self.p))
+        return self.rng_dump_p(seed, t0, count, self.p)
+
+    def rng_dump_p(self, seed, t0, count, p):
+        """The device RNG stream under Philox key `seed`: normals (count, p) and uniforms (count,)
+        for iterations t0 .. t0+count-1 (lrb_rng_dump)."""
+        z = np.empty((count, p))
         u = np.empty(count)
-        self._ck(self._lib.lrb_rng_dump(self._h, int(seed), int(t0), int(count), self.p, N.as_dp(z), N.as_dp(u)))
+        self._ck(self._lib.lrb_rng_dump(self._h, int(seed) & (2 ** 64 - 1), int(t0), int(count), int(p),
+                                        N.as_dp(z), N.as_dp(u)))
         return z, u
 
 
@@ -407,14 +455,24 @@ def _owner(fn, name):
     return None
 
 
-def mhKernel(lpost, rprop, dprop=_unit_dprop):
-    """fit-numpy.py:53-62. With lpost = this module's lpost and rprop a RandomWalk the
-    returned kernel runs on the device; any other callables give the reference's
+def mhKernel(lpost, rprop, dprop=_unit_dprop, threaded=True):
+    """fit-numpy.py:53-62 (threaded=True, the default: kernel(x, ll) -> (x, ll) carries the old
+    log-density along) or fit-np-hmc.py:56-63 (threaded=False: kernel(x) -> x re-evaluates
+    lpost(x) every step; `logreg_b200.np_hmc.mhKernel` is this form, so that script's
+    two-argument call keeps its meaning).  With lpost = this module's lpost and rprop a
+    RandomWalk the threaded kernel runs on the device; any other callables give the reference's
     host-side closure (with the device lpost inside it if that is what was passed)."""
+    if not threaded:
+        def kernel1(x):
+            prop = rprop(x)
+            a = lpost(prop) - lpost(x)
+            if np.log(np.random.rand()) < a:
+                x = prop
+            return x
+        return kernel1
     prob = _owner(lpost, "lpost")
     if prob is not None and isinstance(rprop, RandomWalk) and dprop is _unit_dprop:
         return DeviceKernel(prob, N.RWMH, rprop.scale)
-    # HMC-script variant (fit-np-hmc.py:56-63) is built by hmcKernel; here the threaded one:
     def kernel(x, ll):
         prop = rprop(x)
         lp = lpost(prop)

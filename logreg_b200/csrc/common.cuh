@@ -43,6 +43,15 @@ constexpr uint32_t kStreamNormal = 0u;   // sampler N(0,1) draws
 constexpr uint32_t kStreamUniform = 1u;  // sampler accept uniforms
 constexpr uint32_t kStreamDataX = 2u;    // synthetic design matrix
 constexpr uint32_t kStreamDataY = 3u;    // synthetic responses
+constexpr uint32_t kStreamSplit = 4u;    // key derivation of the keyed (JAX-style) front-end
+
+// Child i of a 64-bit key: words (x, y) of Philox4x32-10 with counter (i_lo, i_hi, 0, kStreamSplit)
+// under the parent key.  This is what logreg_b200.jaxlike.split(key, n)[i] returns
+// (the role of jax.random.split in Python/fit-jax2.py:90,100,109).
+__host__ __device__ inline uint64_t philox_child(uint64_t key, uint64_t i) {
+  Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, kStreamSplit, (uint32_t)key, (uint32_t)(key >> 32));
+  return ((uint64_t)r.y << 32) | (uint64_t)r.x;
+}
 
 // N(0,1) for (iteration t, coordinate j): Box-Muller on two 53-bit uniforms.
 __device__ inline double philox_normal(uint64_t seed, uint64_t t, uint32_t j) {

@@ -50,7 +50,16 @@ struct EvalArgs {
   double* sums;       // [P+1] un-fused output: [ll, gll]
   int fuse_finish;    // 1: run finish_eval in the last CTA; 0: only write `sums`
   FinishArgs fin;
+  long long* timeline;  // development aid (lrb_debug_timeline): %globaltimer stamps, [grid][4] + [8]; else nullptr
 };
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define EV_STAMP(slot) do { if (a.timeline != nullptr && tid == 0) a.timeline[(size_t)blockIdx.x * 4 + (slot)] = global_ns(); } while (0)
+#define EV_STAMP_LAST(slot) do { if (a.timeline != nullptr && tid == 0) a.timeline[(size_t)gridDim.x * 4 + (slot)] = global_ns(); } while (0)
 
 template <typename T> struct Chunk;
 template <> struct Chunk<float> {
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   // CTA is still reducing / running the sampler update.  X never changes, so the first batch
   // is fetched BEFORE waiting for the previous grid (hides launch latency and the DRAM ramp);
   // everything that depends on it (beta, the pause flag, the partials buffer) comes after.
+  EV_STAMP(0);
   vec v[S];
   auto load_batch = [&](long long bt) {
     const long long chunk0 = bt * (S * 32) + lane;
@@ -185,6 +195,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   };
   if (bt0 < nbatch) load_batch(bt0);
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  EV_STAMP(1);
 
   // A paused sampler makes surplus graph nodes no-ops (every CTA sees the same phase:
   // the last CTA only changes it after all CTAs have taken their ticket).
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   }
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // streaming done: let the next grid in
+  EV_STAMP(2);
 
   // ---- CTA reduction
   if constexpr (GRAD) {
@@ -323,8 +335,11 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
   __syncthreads();
   if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
   __syncthreads();
+  EV_STAMP(3);
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
+  if (a.timeline != nullptr && tid == 0) a.timeline[(size_t)gridDim.x * 4 + 4] = a.timeline[(size_t)gridDim.x * 4 + 2];  // previous evaluation's finish
+  EV_STAMP_LAST(0);
   if (tid == 0) *a.ticket = 0u;  // re-arm for the next launch (stream-ordered)
   if (a.fuse_finish) prefetch_finish_inputs(a.fin);
 
@@ -357,8 +372,10 @@ __global__ void __launch_bounds__(kBlock, 2) eval_kernel(const EvalArgs a) {
     tot[c] = s;
   }
   __syncthreads();
+  EV_STAMP_LAST(1);
   if (a.fuse_finish) {
     finish_eval(a.fin, tot, scratch);
+    EV_STAMP_LAST(2);
   } else {
     for (int c = tid; c <= a.fin.p; c += kBlock) a.sums[c] = tot[c];
   }

@@ -18,6 +18,7 @@
 #include "data.cuh"
 #include "eval_kernel.cuh"
 #include "eval_mc_kernel.cuh"
+#include "eval_persist_kernel.cuh"
 #include "eval_tc_kernel.cuh"
 #include "sampler.cuh"
 
@@ -65,11 +66,13 @@ bool load_nccl(const char* path, std::string& err) {
 
 using EvalFn = void (*)(const EvalArgs);
 using EvalMcFn = void (*)(const EvalMcArgs);
+using EvalPersistFn = void (*)(const EvalArgs, const PersistArgs);
 constexpr int kMcChains = 4;   // chains sharing one X batch in the SIMT many-chain kernel
 
 struct KernelChoice {
   EvalFn grad = nullptr, nograd = nullptr;
   EvalMcFn mc = nullptr;
+  EvalPersistFn drive = nullptr, drive_nograd = nullptr;   // drive mode: dynamic scheduling, many evaluations per launch
   int rows_per_batch = 0;
 };
 
@@ -79,6 +82,8 @@ KernelChoice choice() {
   k.grad = eval_kernel<T, P, true>;
   k.nograd = eval_kernel<T, P, false>;
   k.mc = eval_mc_kernel<T, P, kMcChains>;
+  k.drive = eval_persist_kernel<T, P, true>;
+  k.drive_nograd = eval_persist_kernel<T, P, false>;
   k.rows_per_batch = 512 * Chunk<T>::V / P;
   return k;
 }
@@ -128,6 +133,16 @@ struct lrb_handle {
   double* res = nullptr;    // [kMaxP+3]
   double* beta = nullptr;   // [kMaxP]
   double* pinned = nullptr; // host staging [2*kMaxP+8]
+  // drive mode (eval_persist_kernel.cuh): one block of device words [epoch u64][work u32 x2][abort i32][pad][acc f64 x (kMaxP+1)]
+  void* drive_mem = nullptr;
+  unsigned long long* epoch = nullptr;
+  unsigned int* work = nullptr;
+  int* drive_abort = nullptr;
+  double* drive_acc = nullptr;
+  bool drive = true;          // LRB_DRIVE=0 / LRB_DETERMINISTIC=1: static fixed-order kernel, one launch per evaluation
+  int grid_drive = 0, grid_drive_nograd = 0;
+  long long drive_spin_ns = 20ll * 1000 * 1000 * 1000;
+  int drive_static_eighths = -1;  // -1: chosen per shape in configure(); LRB_DRIVE_STATIC overrides
 
   // sampler
   SamplerState* state = nullptr;
@@ -136,6 +151,10 @@ struct lrb_handle {
   double* d_out = nullptr; size_t out_cap = 0;
   double* d_z = nullptr; size_t z_cap = 0;
   double* d_u = nullptr; size_t u_cap = 0;
+  double* d_mom_mean = nullptr; size_t mom_mean_cap = 0;   // [C][p] running means (LRB_RUN_MOMENTS)
+  double* d_mom_m2 = nullptr; size_t mom_m2_cap = 0;       // [C][p][p] running cross-moments
+  bool run_moments = false, run_no_samples = false;
+  bool chain_moments = false;                              // the live chain carries moments
   bool chain_live = false;    // a paused chain exists that a run may continue
   int chain_kind = -1;
   bool run_armed = false;
@@ -161,6 +180,7 @@ struct lrb_handle {
   int* comm_error = nullptr;
   void* peer_base[kMaxRanks] = {};
   bool peer_open[kMaxRanks] = {};
+  long long p2p_timeout_ns = 60ll * 1000 * 1000 * 1000;
 
   // many-chain (C >= 2) state
   SamplerState* states_mc = nullptr;
@@ -180,6 +200,8 @@ struct lrb_handle {
   int tc_min_chains = 12;   // measured crossover, profiles/r1_many_chain_threshold.txt
   bool pdl = true;
   bool l2_persist = true;
+
+  long long* timeline = nullptr;   // lrb_debug_timeline: per-CTA %globaltimer stamps of the latest evaluation
 
   long long kernel_launches = 0, eval_launches = 0;
 };
@@ -214,6 +236,28 @@ int fail(lrb_handle* h, int code, const char* fmt, ...) {
       return fail(h, LRB_E_NCCL, "%s failed: %s", #call,                                  \
                   g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");      \
   } while (0)
+
+// temporary device allocation released on every return path
+struct DevTmp {
+  void* p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// After a synchronisation point of a row-sharded (peer-memory) handle: did an exchange time out?
+// The flag is cleared so the handle stays usable once the group is healthy again.
+int check_comm(lrb_handle* h) {
+  if (h->world <= 1 || h->comm != 2) return LRB_OK;
+  int err = 0;
+  CK(h, cudaMemcpyAsync(&err, h->comm_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (!err) return LRB_OK;
+  CK(h, cudaMemsetAsync(h->comm_error, 0, sizeof(int), h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return fail(h, LRB_E_NCCL, "peer-memory allreduce timed out: a rank of the row-sharded group did not deliver its sums "
+              "(results of this call are NaN)");
+}
 
 int use_device(lrb_handle* h) {
   CK(h, cudaSetDevice(h->device));
@@ -277,6 +321,19 @@ int configure(lrb_handle* h) {
   const long long want = std::max<long long>(1, (nbatch + kWarps - 1) / kWarps);
   h->grid = (int)std::min<long long>((long long)h->sms * occ, want);
   h->grid_nograd = (int)std::min<long long>((long long)h->sms * occ2, want);
+  {
+    int od = 0, odn = 0, coop = 0;
+    CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&od, h->kern.drive, kBlock, 0));
+    CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&odn, h->kern.drive_nograd, kBlock, 0));
+    CK(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    h->grid_drive = (int)std::min<long long>((long long)h->sms * od, want);
+    h->grid_drive_nograd = (int)std::min<long long>((long long)h->sms * odn, want);
+    if (od < 1 || odn < 1 || !coop || nbatch >= (1ll << 31)) h->grid_drive = h->grid_drive_nograd = 0;   // static kernel only
+    // Static share of the schedule (measured, tools/drive_sweep.py): 6/8 when a warp has many
+    // batches (still absorbs SMs up to 33 % slower than average), 4/8 for short passes.
+    if (!getenv("LRB_DRIVE_STATIC"))
+      h->drive_static_eighths = nbatch / std::max<long long>(1, (long long)h->grid_drive * kWarps) >= 32 ? 6 : 4;
+  }
   int occ3 = 0;
   CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, h->kern.mc, kBlock, 0));
   if (occ3 < 1) return fail(h, LRB_E_CUDA, "many-chain kernel does not fit an SM");
@@ -312,9 +369,6 @@ int configure(lrb_handle* h) {
       if (e != cudaSuccess) { cudaGetLastError(); h->tc_ok = false; }
     }
   }
-  if (const char* env = getenv("LRB_TC_MIN_CHAINS")) h->tc_min_chains = atoi(env);
-  if (const char* env = getenv("LRB_PDL")) h->pdl = atoi(env) != 0;
-  if (const char* env = getenv("LRB_L2_PERSIST")) h->l2_persist = atoi(env) != 0;
   apply_l2_policy(h);
   return LRB_OK;
 }
@@ -347,6 +401,7 @@ FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
   f.flags_local = h->flags;
   f.seq = h->seq;
   f.comm_error = h->comm_error;
+  f.timeout_ns = h->p2p_timeout_ns;
   for (int r = 0; r < kMaxRanks; ++r) {
     f.mailbox_peer[r] = nullptr;
     f.flags_peer[r] = nullptr;
@@ -359,8 +414,57 @@ FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
   return f;
 }
 
+bool drive_ok(const lrb_handle* h, bool want_grad) {
+  return h->drive && (want_grad ? h->grid_drive : h->grid_drive_nograd) > 0;
+}
+
+// Drive mode: ONE cooperative launch performs `n_evals` consecutive evaluations (dynamic batch
+// scheduling; with a sampler state the last CTA of each evaluation produces the next point).
+int enqueue_drive(lrb_handle* h, const double* beta, SamplerState* st, bool want_grad, int n_evals) {
+  EvalArgs a{};
+  a.X = h->X; a.y = h->y; a.n = h->n;
+  a.partials = h->partials; a.ticket = h->ticket; a.sums = h->sums;
+  a.fin = finish_args(h, beta, st);
+  a.timeline = h->timeline;
+  const bool nccl_mode = (h->comm == 1 && h->world > 1);
+  a.fuse_finish = nccl_mode ? 0 : 1;
+  if (nccl_mode && n_evals != 1) return fail(h, LRB_E_STATE, "drive mode with NCCL takes one evaluation per launch (internal error)");
+  PersistArgs pa{};
+  pa.epoch = h->epoch; pa.work = h->work; pa.acc = h->drive_acc; pa.abort = h->drive_abort;
+  pa.n_evals = n_evals; pa.spin_limit_ns = h->drive_spin_ns;
+  pa.static_eighths = h->drive_static_eighths;
+  void* fn = (void*)(want_grad ? h->kern.drive : h->kern.drive_nograd);
+  const int grid = want_grad ? h->grid_drive : h->grid_drive_nograd;
+  void* args[2] = {&a, &pa};
+  CK(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, 0, h->stream));
+  h->kernel_launches++;
+  h->eval_launches += n_evals;
+  if (nccl_mode) {
+    CKN(h, g_nccl.AllReduce(h->sums, h->sums, (size_t)h->p + 1, ncclDouble, ncclSum, h->nccl, h->stream));
+    finish_kernel<<<1, kBlock, 0, h->stream>>>(a.fin, h->sums);
+    CK(h, cudaGetLastError());
+    h->kernel_launches++;
+  }
+  return LRB_OK;
+}
+
+// After a synchronisation: did a drive-mode launch abandon a wait?  Leaves the counters clean.
+int check_drive(lrb_handle* h) {
+  int ab = 0;
+  CK(h, cudaMemcpyAsync(&ab, h->drive_abort, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (!ab) return LRB_OK;
+  CK(h, cudaMemset(h->work, 0, 2 * sizeof(unsigned int)));
+  CK(h, cudaMemset(h->drive_abort, 0, sizeof(int)));
+  CK(h, cudaMemset(h->drive_acc, 0, (kMaxP + 1) * sizeof(double)));
+  CK(h, cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  h->chain_live = false;
+  return fail(h, LRB_E_STATE, "drive-mode kernel abandoned a wait (a CTA or a peer rank did not arrive); the run is void");
+}
+
 // Enqueue one fused evaluation at `beta` (device) on h->stream.
 int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_grad) {
+  if (drive_ok(h, want_grad)) return enqueue_drive(h, beta, st, want_grad, 1);
   EvalArgs a{};
   a.X = h->X;
   a.y = h->y;
@@ -369,6 +473,7 @@ int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_
   a.ticket = h->ticket;
   a.sums = h->sums;
   a.fin = finish_args(h, beta, st);
+  a.timeline = h->timeline;
   const bool nccl_mode = (h->comm == 1 && h->world > 1);
   a.fuse_finish = nccl_mode ? 0 : 1;
   EvalFn fn = want_grad ? h->kern.grad : h->kern.nograd;
@@ -487,6 +592,24 @@ extern "C" int lrb_create(int device, lrb_handle** out) {
   CKC(cudaMalloc(&h->comm_error, sizeof(int)));
   CKC(cudaMemset(h->comm_error, 0, sizeof(int)));
   CKC(cudaMallocHost(&h->pinned, (2 * kMaxP + 8) * sizeof(double)));
+  {
+    const size_t bytes = 32 + (kMaxP + 1) * sizeof(double);
+    CKC(cudaMalloc(&h->drive_mem, bytes));
+    CKC(cudaMemset(h->drive_mem, 0, bytes));
+    char* b = reinterpret_cast<char*>(h->drive_mem);
+    h->epoch = reinterpret_cast<unsigned long long*>(b);
+    h->work = reinterpret_cast<unsigned int*>(b + 8);
+    h->drive_abort = reinterpret_cast<int*>(b + 16);
+    h->drive_acc = reinterpret_cast<double*>(b + 32);
+  }
+  // development / A-B knobs (the supported interface is lrb_set_option)
+  if (const char* env = getenv("LRB_TC_MIN_CHAINS")) h->tc_min_chains = atoi(env);
+  if (const char* env = getenv("LRB_PDL")) h->pdl = atoi(env) != 0;
+  if (const char* env = getenv("LRB_P2P_TIMEOUT_MS")) h->p2p_timeout_ns = std::max(1ll, atoll(env)) * 1000000ll;
+  if (const char* env = getenv("LRB_L2_PERSIST")) h->l2_persist = atoi(env) != 0;
+  if (const char* env = getenv("LRB_DRIVE")) h->drive = atoi(env) != 0;
+  if (const char* env = getenv("LRB_DRIVE_STATIC")) h->drive_static_eighths = std::min(8, std::max(0, atoi(env)));
+  if (const char* env = getenv("LRB_DETERMINISTIC")) { if (atoi(env) != 0) h->drive = false; }
 #undef CKC
   *out = h;
   return LRB_OK;
@@ -503,7 +626,8 @@ extern "C" int lrb_destroy(lrb_handle* h) {
   free_data(h);
   void* bufs[] = {h->d_pscale, h->d_logps, h->partials, h->ticket, h->sums, h->res, h->beta, h->d_init,
                   h->d_scale, h->state, h->seq, h->comm_error, h->d_out, h->d_z, h->d_u, h->mailbox,
-                  h->states_mc, h->sums_mc, h->res_mc, h->beta_mc, h->partials_tc};
+                  h->states_mc, h->sums_mc, h->res_mc, h->beta_mc, h->partials_tc, h->timeline, h->drive_mem,
+                  h->d_mom_mean, h->d_mom_m2};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -523,11 +647,30 @@ extern "C" int lrb_set_stream(lrb_handle* h, void* cuda_stream) {
   return LRB_OK;
 }
 
+extern "C" int lrb_set_option(lrb_handle* h, int option, int64_t value) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  switch (option) {
+    case LRB_OPT_DETERMINISTIC: h->drive = value == 0; break;
+    case LRB_OPT_TC_MIN_CHAINS: h->tc_min_chains = (int)std::max<int64_t>(1, value); break;
+    case LRB_OPT_P2P_TIMEOUT_MS:
+      h->p2p_timeout_ns = std::max<int64_t>(1, value) * 1000000ll;
+      h->drive_spin_ns = h->p2p_timeout_ns;
+      break;
+    case LRB_OPT_PDL: h->pdl = value != 0; break;
+    case LRB_OPT_L2_PERSIST: h->l2_persist = value != 0; if (h->bound) apply_l2_policy(h); break;
+    default: return fail(h, LRB_E_BAD_ARG, "unknown option %d", option);
+  }
+  drop_graph(h);
+  return LRB_OK;
+}
+
 extern "C" int lrb_synchronize(lrb_handle* h) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
   if (use_device(h)) return LRB_E_CUDA;
   CK(h, cudaStreamSynchronize(h->stream));
-  return LRB_OK;
+  return check_comm(h);   // the synchronisation point of lrb_eval_device on a row-sharded handle
 }
 
 extern "C" int lrb_get_info(const lrb_handle* h, lrb_info* info) {
@@ -568,53 +711,52 @@ extern "C" int lrb_bind_data(lrb_handle* h, const void* X, int x_dtype, int layo
     // stage row blocks (<= 256 MB) through device memory, re-laying each out
     long long chunk = std::max<long long>(1, (256ll << 20) / ((long long)p * (long long)es));
     chunk = std::min<long long>(chunk, n);
-    void* stage = nullptr;
-    CK(h, cudaMalloc(&stage, (size_t)chunk * p * es));
+    DevTmp stage_buf;
+    CK(h, stage_buf.alloc((size_t)chunk * p * es));
+    void* stage = stage_buf.p;
     for (long long r0 = 0; r0 < n; r0 += chunk) {
       const long long nr = std::min<long long>(chunk, n - r0);
-      cudaError_t e;
       if (colmajor)
-        e = cudaMemcpy2DAsync(stage, (size_t)nr * es, (const char*)X + (size_t)r0 * es, (size_t)ld * es,
-                              (size_t)nr * es, (size_t)p, cudaMemcpyHostToDevice, h->stream);
+        CK(h, cudaMemcpy2DAsync(stage, (size_t)nr * es, (const char*)X + (size_t)r0 * es, (size_t)ld * es,
+                                (size_t)nr * es, (size_t)p, cudaMemcpyHostToDevice, h->stream));
       else
-        e = cudaMemcpy2DAsync(stage, (size_t)p * es, (const char*)X + (size_t)r0 * ld * es, (size_t)ld * es,
-                              (size_t)p * es, (size_t)nr, cudaMemcpyHostToDevice, h->stream);
-      if (e != cudaSuccess) { cudaFree(stage); return fail(h, LRB_E_CUDA, "X upload failed: %s", cudaGetErrorString(e)); }
+        CK(h, cudaMemcpy2DAsync(stage, (size_t)p * es, (const char*)X + (size_t)r0 * ld * es, (size_t)ld * es,
+                                (size_t)p * es, (size_t)nr, cudaMemcpyHostToDevice, h->stream));
       const long long sld = colmajor ? nr : p;
       rc = x_dtype == LRB_F32 ? ingest_any<float>(h, (const float*)stage, colmajor, sld, nr, r0)
                               : ingest_any<double>(h, (const double*)stage, colmajor, sld, nr, r0);
-      if (rc) { cudaFree(stage); return rc; }
-      e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) { cudaFree(stage); return fail(h, LRB_E_CUDA, "X ingest failed: %s", cudaGetErrorString(e)); }
+      if (rc) return rc;
+      CK(h, cudaStreamSynchronize(h->stream));
     }
-    cudaFree(stage);
   }
 
   // y -> u8 with validation
-  int* d_bad = nullptr;
-  CK(h, cudaMalloc(&d_bad, sizeof(int)));
+  if (y_dtype != LRB_F32 && y_dtype != LRB_F64 && y_dtype != LRB_U8) return fail(h, LRB_E_BAD_ARG, "bad y dtype");
+  DevTmp bad_buf, ystage;
+  CK(h, bad_buf.alloc(sizeof(int)));
+  int* d_bad = bad_buf.as<int>();
   CK(h, cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
   const size_t ys = y_dtype == LRB_F32 ? 4 : y_dtype == LRB_F64 ? 8 : 1;
-  if (y_dtype != LRB_F32 && y_dtype != LRB_F64 && y_dtype != LRB_U8) { cudaFree(d_bad); return fail(h, LRB_E_BAD_ARG, "bad y dtype"); }
   const void* ysrc = y;
-  void* ystage = nullptr;
   if (location == LRB_HOST) {
-    CK(h, cudaMalloc(&ystage, (size_t)n * ys));
-    CK(h, cudaMemcpyAsync(ystage, y, (size_t)n * ys, cudaMemcpyHostToDevice, h->stream));
-    ysrc = ystage;
+    CK(h, ystage.alloc((size_t)n * ys));
+    CK(h, cudaMemcpyAsync(ystage.p, y, (size_t)n * ys, cudaMemcpyHostToDevice, h->stream));
+    ysrc = ystage.p;
   }
   const unsigned gy = (unsigned)((n + 255) / 256);
   if (y_dtype == LRB_F32) ingest_y_kernel<float><<<gy, 256, 0, h->stream>>>((const float*)ysrc, n, h->y, d_bad);
   else if (y_dtype == LRB_F64) ingest_y_kernel<double><<<gy, 256, 0, h->stream>>>((const double*)ysrc, n, h->y, d_bad);
   else ingest_y_kernel<uint8_t><<<gy, 256, 0, h->stream>>>((const uint8_t*)ysrc, n, h->y, d_bad);
+  CK(h, cudaGetLastError());
   h->kernel_launches++;
   int bad = 0;
-  cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (ystage) cudaFree(ystage);
-  cudaFree(d_bad);
-  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "y ingest failed: %s", cudaGetErrorString(e));
-  if (bad) { free_data(h); return fail(h, LRB_E_BAD_ARG, "y must contain only 0 and 1"); }
+  CK(h, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (bad) {
+    free_data(h);
+    h->n = 0; h->p = 0; h->P = 0; h->kern = KernelChoice{};
+    return fail(h, LRB_E_BAD_ARG, "y must contain only 0 and 1");
+  }
   rc = configure(h);
   if (rc) return rc;
   h->bound = true;
@@ -631,8 +773,9 @@ extern "C" int lrb_gen_synthetic(lrb_handle* h, int64_t n_local, int p, int mode
   if (rc) return rc;
   rc = set_prior(h, pscale);
   if (rc) return rc;
-  double* d_bt = nullptr;
-  CK(h, cudaMalloc(&d_bt, kMaxP * sizeof(double)));
+  DevTmp bt_buf;
+  CK(h, bt_buf.alloc(kMaxP * sizeof(double)));
+  double* d_bt = bt_buf.as<double>();
   CK(h, cudaMemcpyAsync(d_bt, beta_true, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const long long nthreads = n_local * (h->P / 4);
   const unsigned gx = (unsigned)((nthreads + 255) / 256), gy = (unsigned)((n_local + 255) / 256);
@@ -644,10 +787,8 @@ extern "C" int lrb_gen_synthetic(lrb_handle* h, int64_t n_local, int p, int mode
     synth_y_kernel<double><<<gy, 256, 0, h->stream>>>((const double*)h->X, n_local, p, h->P, d_bt, seed, row_offset, h->y);
   }
   h->kernel_launches += 2;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_bt);
-  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "synthetic generation failed: %s", cudaGetErrorString(e));
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
   rc = configure(h);
   if (rc) return rc;
   h->bound = true;
@@ -660,21 +801,20 @@ extern "C" int lrb_copy_rows(lrb_handle* h, int64_t row0, int64_t nrows, double*
   if (row0 < 0 || nrows < 0 || row0 + nrows > h->n) return fail(h, LRB_E_BAD_ARG, "row range out of bounds");
   if (nrows == 0) return LRB_OK;
   if (use_device(h)) return LRB_E_CUDA;
-  double* dX = nullptr; float* dy = nullptr;
-  CK(h, cudaMalloc(&dX, (size_t)nrows * h->p * sizeof(double)));
-  CK(h, cudaMalloc(&dy, (size_t)nrows * sizeof(float)));
+  DevTmp bx, by;
+  CK(h, bx.alloc((size_t)nrows * h->p * sizeof(double)));
+  CK(h, by.alloc((size_t)nrows * sizeof(float)));
+  double* dX = bx.as<double>(); float* dy = by.as<float>();
   const unsigned g = (unsigned)((nrows * h->P + 255) / 256);
   if (h->mode == LRB_MODE_FP32)
     export_rows_kernel<float><<<g, 256, 0, h->stream>>>((const float*)h->X, h->y, row0, nrows, h->p, h->P, dX, dy);
   else
     export_rows_kernel<double><<<g, 256, 0, h->stream>>>((const double*)h->X, h->y, row0, nrows, h->p, h->P, dX, dy);
   h->kernel_launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(X_out, dX, (size_t)nrows * h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(y_out, dy, (size_t)nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(dX); cudaFree(dy);
-  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "copy_rows failed: %s", cudaGetErrorString(e));
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(X_out, dX, (size_t)nrows * h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(y_out, dy, (size_t)nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return LRB_OK;
 }
 
@@ -684,6 +824,11 @@ namespace {
 // states / results / sums for C chains
 int ensure_chains(lrb_handle* h, int C) {
   if (C <= h->mc_cap) return LRB_OK;
+  // The launch graph bakes these pointers into its kernel arguments and a paused many-chain run
+  // lives in states_mc: both die with the reallocation.
+  CK(h, cudaStreamSynchronize(h->stream));
+  drop_graph(h);
+  if (h->chain_C > 1) { h->chain_live = false; h->run_armed = false; }
   if (h->states_mc) cudaFree(h->states_mc);
   if (h->sums_mc) cudaFree(h->sums_mc);
   if (h->res_mc) cudaFree(h->res_mc);
@@ -710,6 +855,8 @@ int reserve_tc(lrb_handle* h, int C) {
   const int gx = std::max(1, std::min(h->sms / groups, ntiles));
   const size_t need = (size_t)gx * groups * (h->P + kTcSub) * kTcChains;
   if (need <= h->partials_tc_cap) return LRB_OK;
+  CK(h, cudaStreamSynchronize(h->stream));
+  drop_graph(h);   // captured tensor-core launches hold the old scratch pointer
   if (h->partials_tc) cudaFree(h->partials_tc);
   h->partials_tc = nullptr; h->partials_tc_cap = 0;
   CK(h, cudaMalloc(&h->partials_tc, need * sizeof(double)));
@@ -818,6 +965,7 @@ extern "C" int lrb_eval(lrb_handle* h, const double* beta, int C, int want_grad,
     double* back = h->pinned + kMaxP;
     CK(h, cudaMemcpyAsync(back, h->res, (size_t)(p + 3) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if ((rc = check_comm(h))) return rc;
     if (lpost) lpost[c] = back[0];
     if (ll) ll[c] = back[1];
     if (glp && want_grad) std::memcpy(glp + (size_t)c * p, back + 3, p * sizeof(double));
@@ -873,24 +1021,50 @@ extern "C" int lrb_debug_tc_eta(lrb_handle* h, const double* beta, int C, float*
   return LRB_OK;
 }
 
+// Development aid: record %globaltimer stamps of every CTA of the fused kernel (entry, after the
+// grid dependency, end of streaming, after the ticket) and of the last CTA's tail.  The stamps of
+// the LATEST evaluation are kept.
+extern "C" int lrb_debug_timeline(lrb_handle* h, int enable) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  drop_graph(h);
+  if (h->timeline) { cudaFree(h->timeline); h->timeline = nullptr; }
+  if (enable) {
+    const size_t cnt = (size_t)h->sms * 8 * 4 + 8;
+    CK(h, cudaMalloc(&h->timeline, cnt * sizeof(long long)));
+    CK(h, cudaMemset(h->timeline, 0, cnt * sizeof(long long)));
+  }
+  return LRB_OK;
+}
+
+extern "C" int lrb_debug_timeline_read(lrb_handle* h, int64_t* out, int64_t cap, int64_t* grid) {
+  if (!h || !out || !grid) return fail(h, LRB_E_BAD_ARG, "NULL argument");
+  if (!h->timeline) return fail(h, LRB_E_STATE, "timeline not enabled");
+  if (use_device(h)) return LRB_E_CUDA;
+  const int64_t cnt = (int64_t)h->grid * 4 + 8;
+  if (cap < cnt) return fail(h, LRB_E_BAD_ARG, "out too small: need %lld", (long long)cnt);
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaMemcpy(out, h->timeline, cnt * sizeof(long long), cudaMemcpyDeviceToHost));
+  *grid = h->grid;
+  return LRB_OK;
+}
+
 extern "C" int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
   if (!h->bound) return fail(h, LRB_E_STATE, "lrb_lprior before lrb_bind_data / lrb_gen_synthetic");
   if (!beta || !out || C < 1) return fail(h, LRB_E_BAD_ARG, "bad arguments");
   if (use_device(h)) return LRB_E_CUDA;
-  double *db = nullptr, *dout = nullptr;
-  CK(h, cudaMalloc(&db, (size_t)C * h->p * sizeof(double)));
-  CK(h, cudaMalloc(&dout, (size_t)C * sizeof(double)));
-  cudaError_t e = cudaMemcpyAsync(db, beta, (size_t)C * h->p * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) {
-    prior_kernel<<<C, kBlock, 0, h->stream>>>(db, h->d_pscale, h->d_logps, h->p, dout);
-    h->kernel_launches++;
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(db); cudaFree(dout);
-  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "lprior failed: %s", cudaGetErrorString(e));
+  DevTmp bb, bo;
+  CK(h, bb.alloc((size_t)C * h->p * sizeof(double)));
+  CK(h, bo.alloc((size_t)C * sizeof(double)));
+  double *db = bb.as<double>(), *dout = bo.as<double>();
+  CK(h, cudaMemcpyAsync(db, beta, (size_t)C * h->p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  prior_kernel<<<C, kBlock, 0, h->stream>>>(db, h->d_pscale, h->d_logps, h->p, dout);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  CK(h, cudaMemcpyAsync(out, dout, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return LRB_OK;
 }
 
@@ -950,7 +1124,9 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   if (thin < 1 || iters < 0) return fail(h, LRB_E_BAD_ARG, "thin must be >= 1 and iters >= 0");
   if (kind == LRB_HMC && params->l < 1) return fail(h, LRB_E_BAD_ARG, "HMC needs l >= 1");
   if (kind != LRB_RWMH && !(params->step > 0.0)) return fail(h, LRB_E_BAD_ARG, "step (dt / eps) must be > 0");
-  if (params->rng != LRB_RNG_PHILOX && params->rng != LRB_RNG_REPLAY) return fail(h, LRB_E_BAD_ARG, "bad rng %d", params->rng);
+  if (params->rng != LRB_RNG_PHILOX && params->rng != LRB_RNG_REPLAY && params->rng != LRB_RNG_KEYED)
+    return fail(h, LRB_E_BAD_ARG, "bad rng %d", params->rng);
+  if ((params->flags & LRB_RUN_SET_T0) && params->t0 < 0) return fail(h, LRB_E_BAD_ARG, "t0 must be >= 0");
   if (params->rng == LRB_RNG_REPLAY && (!replay_z || (kind != LRB_UL && !replay_u)))
     return fail(h, LRB_E_BAD_ARG, "replay rng needs replay_z (and replay_u unless UL)");
   if (!init && (!h->chain_live || h->chain_kind != kind || h->chain_C != C))
@@ -964,7 +1140,17 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   int rc;
   if (C > 1 && (rc = ensure_chains(h, C))) return rc;
   if (C > 1 && (rc = reserve_tc(h, C))) return rc;
-  if ((rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)C * iters * p)))) return rc;
+  const bool want_moments = (params->flags & LRB_RUN_MOMENTS) != 0;
+  const bool no_samples = (params->flags & LRB_RUN_NO_SAMPLES) != 0;
+  if (!no_samples && (rc = grow(h, &h->d_out, &h->out_cap, std::max<size_t>(1, (size_t)C * iters * p)))) return rc;
+  if (want_moments) {
+    if (init) {
+      if ((rc = grow(h, &h->d_mom_mean, &h->mom_mean_cap, (size_t)C * p))) return rc;
+      if ((rc = grow(h, &h->d_mom_m2, &h->mom_m2_cap, (size_t)C * p * p))) return rc;
+    } else if (!h->chain_moments) {
+      return fail(h, LRB_E_STATE, "LRB_RUN_MOMENTS on a continued run needs a chain that was started with it");
+    }
+  }
   const double *dz = nullptr, *du = nullptr;
   if (params->rng == LRB_RNG_REPLAY && steps > 0) {
     if ((rc = grow(h, &h->d_z, &h->z_cap, (size_t)C * steps * p))) return rc;
@@ -997,7 +1183,11 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   h->run_C = C;
   sampler_begin_kernel<<<C, kBlock, 0, h->stream>>>(run_states(h), d_init, h->d_scale, kind, params->l, p,
                                                     params->rng, params->step, params->seed,
-                                                    params->init_lpost, steps, thin, dz, du, h->d_out, reuse);
+                                                    params->init_lpost, steps, thin, dz, du,
+                                                    no_samples ? nullptr : h->d_out, reuse,
+                                                    (params->flags & LRB_RUN_SET_T0) ? (long long)params->t0 : 0ll,
+                                                    want_moments ? h->d_mom_mean : nullptr,
+                                                    want_moments ? h->d_mom_m2 : nullptr);
   CK(h, cudaGetLastError());
   h->kernel_launches++;
   CK(h, cudaStreamSynchronize(h->stream));  // staging buffers are reused by the caller's next call
@@ -1007,12 +1197,15 @@ int arm_run(lrb_handle* h, const lrb_sampler_params* params, const double* init,
   h->run_want_grad = kind != LRB_RWMH;
   h->run_thin = thin;
   h->run_iters = iters;
+  h->run_moments = want_moments;
+  h->run_no_samples = no_samples;
+  if (init) h->chain_moments = want_moments;
   h->pending_init_eval = init != nullptr && !reuse && (kind == LRB_MALA || kind == LRB_HMC) && steps > 0;
   h->run_dz = dz;
   h->run_du = du;
   h->run_consumed = false;
   h->run_armed = true;
-  h->chain_live = true;
+  if (init) h->chain_live = false;   // the old chain is overwritten; the new one exists once it has been launched
   h->chain_kind = kind;
   h->chain_C = C;
   return LRB_OK;
@@ -1029,13 +1222,28 @@ int launch_run(lrb_handle* h) {
     sampler_begin_kernel<<<h->run_C, kBlock, 0, h->stream>>>(run_states(h), nullptr, h->d_scale, h->run_kind,
                                                              h->run_params.l, h->p, h->run_params.rng,
                                                              h->run_params.step, h->run_params.seed, 0.0, steps,
-                                                             h->run_thin, h->run_dz, h->run_du, h->d_out, 0);
+                                                             h->run_thin, h->run_dz, h->run_du,
+                                                             h->run_no_samples ? nullptr : h->d_out, 0, 0ll,
+                                                             h->run_moments ? h->d_mom_mean : nullptr,
+                                                             h->run_moments ? h->d_mom_m2 : nullptr);
     CK(h, cudaGetLastError());
     h->kernel_launches++;
   }
   h->run_consumed = true;
   long long needed = steps * evals_per_step(h->run_kind, h->run_l) + (h->pending_init_eval ? 1 : 0);
   h->pending_init_eval = false;
+  const bool nccl_mode = (h->comm == 1 && h->world > 1);
+  if (h->run_C == 1 && !nccl_mode && drive_ok(h, h->run_want_grad)) {
+    // drive mode: the whole run is one launch (chunked only to keep the counter in an int)
+    while (needed > 0) {
+      const int chunk = (int)std::min<long long>(needed, 1ll << 24);
+      int rc = enqueue_drive(h, h->state->beta_in, h->state, h->run_want_grad, chunk);
+      if (rc) return rc;
+      needed -= chunk;
+    }
+    h->chain_live = true;
+    return LRB_OK;
+  }
   // graph of up to 64 evaluations, replayed; the remainder goes out as plain launches
   const int nodes = (int)std::min<long long>(64, needed);
   int rc = build_graph(h, nodes, h->run_want_grad);
@@ -1048,6 +1256,7 @@ int launch_run(lrb_handle* h) {
   }
   for (; needed > 0; --needed)
     if ((rc = enqueue_run_eval(h))) return rc;
+  h->chain_live = true;
   return LRB_OK;
 }
 
@@ -1056,18 +1265,18 @@ int finish_run(lrb_handle* h, double* out, int64_t* accepted) {
   if (use_device(h)) return LRB_E_CUDA;
   const int C = h->run_C;
   const size_t cnt = (size_t)C * h->run_iters * h->p;
-  if (out && cnt) CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out && cnt && !h->run_no_samples)
+    CK(h, cudaMemcpyAsync(out, h->d_out, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   std::vector<long long> acc(C, 0);
   std::vector<int> phase(C, -1);
-  int comm_err = 0;
-  CK(h, cudaMemcpyAsync(&comm_err, h->comm_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SamplerState* st = run_states(h);
   CK(h, cudaMemcpy2DAsync(acc.data(), sizeof(long long), &st->accepted, sizeof(SamplerState), sizeof(long long), C,
                           cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpy2DAsync(phase.data(), sizeof(int), &st->phase, sizeof(SamplerState), sizeof(int), C,
                           cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  if (comm_err) return fail(h, LRB_E_NCCL, "peer-memory allreduce timed out: a rank of the row-sharded group did not deliver its sums");
+  if (int rcc = check_comm(h)) return rcc;
+  if (int rcd = check_drive(h)) return rcd;
   for (int c = 0; c < C; ++c) {
     if (accepted) accepted[c] = acc[c];
     if (phase[c] != PH_PAUSED)
@@ -1147,22 +1356,47 @@ extern "C" int lrb_run(lrb_handle* h, const lrb_sampler_params* params, const do
   return LRB_OK;
 }
 
+extern "C" int lrb_run_moments(lrb_handle* h, int pooled, int64_t* count, double* mean, double* cov) {
+  if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
+  if (!count || !mean) return fail(h, LRB_E_BAD_ARG, "count / mean is NULL");
+  if (!h->chain_live || !h->chain_moments) return fail(h, LRB_E_STATE, "no run with LRB_RUN_MOMENTS on this handle");
+  if (use_device(h)) return LRB_E_CUDA;
+  const int C = h->chain_C, p = h->p;
+  const int rows = pooled ? 1 : C;
+  DevTmp bc, bm, bv;
+  CK(h, bc.alloc((size_t)rows * sizeof(long long)));
+  CK(h, bm.alloc((size_t)rows * p * sizeof(double)));
+  if (cov) CK(h, bv.alloc((size_t)rows * p * p * sizeof(double)));
+  SamplerState* st = C > 1 ? h->states_mc : h->state;
+  moments_out_kernel<<<rows, kBlock, 0, h->stream>>>(st, C, p, pooled ? 1 : 0, bc.as<long long>(), bm.as<double>(),
+                                                     cov ? bv.as<double>() : nullptr);
+  CK(h, cudaGetLastError());
+  h->kernel_launches++;
+  static_assert(sizeof(long long) == sizeof(int64_t), "count layout");
+  CK(h, cudaMemcpyAsync(count, bc.p, (size_t)rows * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(mean, bm.p, (size_t)rows * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (cov) CK(h, cudaMemcpyAsync(cov, bv.p, (size_t)rows * p * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return LRB_OK;
+}
+
+extern "C" uint64_t lrb_key_child(uint64_t key, uint64_t i) { return philox_child(key, i); }
+
 extern "C" int lrb_rng_dump(lrb_handle* h, uint64_t seed, int64_t t0, int64_t count, int p,
                             double* z_out, double* u_out) {
   if (!h) return fail(nullptr, LRB_E_BAD_ARG, "handle is NULL");
   if (count < 1 || p < 1 || !z_out || !u_out) return fail(h, LRB_E_BAD_ARG, "bad arguments");
   if (use_device(h)) return LRB_E_CUDA;
-  double *dz = nullptr, *du = nullptr;
-  CK(h, cudaMalloc(&dz, (size_t)count * p * sizeof(double)));
-  CK(h, cudaMalloc(&du, (size_t)count * sizeof(double)));
+  DevTmp bz, bu;
+  CK(h, bz.alloc((size_t)count * p * sizeof(double)));
+  CK(h, bu.alloc((size_t)count * sizeof(double)));
+  double *dz = bz.as<double>(), *du = bu.as<double>();
   rng_dump_kernel<<<(unsigned)((count * p + 255) / 256), 256, 0, h->stream>>>(seed, t0, count, p, dz, du);
   h->kernel_launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(z_out, dz, (size_t)count * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(u_out, du, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(dz); cudaFree(du);
-  if (e != cudaSuccess) return fail(h, LRB_E_CUDA, "rng_dump failed: %s", cudaGetErrorString(e));
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(z_out, dz, (size_t)count * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(u_out, du, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return LRB_OK;
 }
 
@@ -1214,6 +1448,16 @@ extern "C" int lrb_comm_p2p_connect(lrb_handle* h, int rank, int world, const vo
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(h, LRB_E_BAD_ARG, "bad rank/world %d/%d", rank, world);
   if (!h->mailbox) return fail(h, LRB_E_STATE, "call lrb_comm_p2p_export first");
   if (use_device(h)) return LRB_E_CUDA;
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < kMaxRanks; ++r) {   // a reconnect: drop the previous mappings
+    if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    h->peer_open[r] = false; h->peer_base[r] = nullptr;
+  }
+  // Stale sums / flags of a previous connection would satisfy the first acquire waits: start clean.
+  // The caller must barrier between connect and the first evaluation (dist.init_comm does), so no
+  // peer has written yet.
+  CK(h, cudaMemset(h->mailbox, 0, kMailBytes));
+  CK(h, cudaMemset(h->comm_error, 0, sizeof(int)));
   for (int r = 0; r < world; ++r) {
     if (r == rank) { h->peer_base[r] = h->mailbox; continue; }
     cudaIpcMemHandle_t mh;

@@ -25,16 +25,31 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     # the ctypes table covers the header exactly (nothing bound that is not declared, and vice versa)
     assert sorted(N.SIGNATURES) == names
-    assert lib.lrb_abi_version() == 1
+    assert lib.lrb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from logreg_b200 import _native as N
-    # lrb_sampler_params: int32 int32 double ptr uint64 int32 int32 double = 48 bytes on LP64
-    assert C.sizeof(N.SamplerParams) == 48
+    # lrb_sampler_params: int32 int32 double ptr uint64 int32 int32 double int64 = 56 bytes on LP64 (ABI 2 added t0)
+    assert C.sizeof(N.SamplerParams) == 56
     assert N.SamplerParams.scale.offset == 16 and N.SamplerParams.flags.offset == 36 and N.SamplerParams.init_lpost.offset == 40
+    assert N.SamplerParams.t0.offset == 48
     # lrb_info: int64 + 8*int32 + 3*int64 = 64 bytes
     assert C.sizeof(N.Info) == 64 and N.Info.bytes_per_eval.offset == 40
+
+
+def test_key_child_is_host_arithmetic_and_matches_the_philox_spec():
+    """lrb_key_child (the split of the keyed front-end) needs no GPU and equals words (x, y) of
+    Philox4x32-10 at counter (i_lo, i_hi, 0, 4) under the parent key."""
+    from logreg_b200 import _native as N
+    from tests.test_host_logic import philox_ref
+    lib = N.load()
+    for key in (0, 42, 0xDEADBEEFCAFEF00D, 2 ** 64 - 1):
+        for i in (0, 1, 7, 2 ** 32 + 5):
+            r = philox_ref([i & 0xFFFFFFFF, i >> 32, 0, 4], [key & 0xFFFFFFFF, key >> 32])
+            assert lib.lrb_key_child(key, i) == ((r[1] << 32) | r[0])
+    import logreg_b200.jaxlike as J
+    assert J.split(42, 4) == [lib.lrb_key_child(42, i) for i in range(4)]
 
 
 def test_no_gpu_means_loud_failure():

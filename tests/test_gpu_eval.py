@@ -219,7 +219,8 @@ def test_bind_from_device_tensors(lr, synth):
     """LRB_DEVICE location: data owned by torch on the GPU, every layout / dtype combination."""
     import torch
     X32 = synth["X32"]
-    ref = lr.Problem().bind_data(X32, synth["y"], synth["pscale"], mode="fp32")
+    # deterministic=True: fixed-order static kernel, so identical device data => identical bits
+    ref = lr.Problem(deterministic=True).bind_data(X32, synth["y"], synth["pscale"], mode="fp32")
     b = synth["B"][1]
     want = ref.eval(b)
     Xt = torch.from_numpy(X32).cuda()
@@ -227,7 +228,7 @@ def test_bind_from_device_tensors(lr, synth):
     variants = [(Xt, yt), (Xt.t().contiguous().t(), yt), (Xt.double(), yt.double()),
                 (torch.cat([Xt, Xt], dim=1)[:, :32], yt.to(torch.uint8))]
     for Xv, yv in variants:
-        got = lr.Problem().bind_torch(Xv, yv, synth["pscale"], mode="fp32").eval(b)
+        got = lr.Problem(deterministic=True).bind_torch(Xv, yv, synth["pscale"], mode="fp32").eval(b)
         assert got[0] == want[0] and got[1] == want[1]
         np.testing.assert_array_equal(got[2], want[2])
     got64 = lr.Problem().bind_torch(Xt.double(), yt, synth["pscale"], mode="fp64").eval(b)
@@ -243,8 +244,8 @@ def test_chunked_host_ingest_col_major_equals_row_major(lr):
     Xc[:, 0] = 1.0
     bt = rs.randn(p) / 8
     y = (rs.rand(n) < 1 / (1 + np.exp(-Xc.dot(bt)))).astype(np.float32)
-    a = lr.Problem().bind_data(Xc, y, np.ones(p), mode="fp64")
-    f = lr.Problem().bind_data(np.asfortranarray(Xc), y, np.ones(p), mode="fp64")
+    a = lr.Problem(deterministic=True).bind_data(Xc, y, np.ones(p), mode="fp64")
+    f = lr.Problem(deterministic=True).bind_data(np.asfortranarray(Xc), y, np.ones(p), mode="fp64")
     ra, rf = a.eval(bt), f.eval(bt)
     assert ra[0] == rf[0]
     np.testing.assert_array_equal(ra[2], rf[2])

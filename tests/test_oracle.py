@@ -201,3 +201,31 @@ def test_oracle_row_additivity_hypothesis(synth):
         np.testing.assert_allclose(g, full_g, rtol=1e-9, atol=1e-9)
 
     check()
+
+
+def test_pima_mala_tuning_is_chaotic_even_for_the_oracle(pima):
+    """Why whole-chain parity for the reference's Pima MALA tuning (dt=1e-5, pre=[100,1,..,25,1],
+    fit-np-mala.py:97-99) is stated on a prefix plus one-step-ahead: the map amplifies rounding.
+    The oracle itself, fed the reference's own draws, reproduces the reference chain bit for bit
+    with the reference's column-major X, but with the SAME numbers stored row-major (a different
+    BLAS summation order in X.dot / X.T.dot, ~1e-16 relative) it leaves the reference trajectory
+    after a few dozen steps.  A GPU kernel has yet another summation order, so the same happens."""
+    Z, U, ref = pima["mala_t1_Z"], pima["mala_t1_U"], pima["mala_t1_mat"]
+    out = {}
+    for name, X in (("F", np.asfortranarray(pima["X"])), ("C", np.ascontiguousarray(pima["X"]))):
+        tgt = O.Target(X, pima["y"], pima["pscale"])
+        rng = O.ReplayRNG(Z, U)
+        k = O.mala_kernel(tgt.lpost, tgt.glp, 8, dt=1e-5, pre=pima["pre"], rng=rng)
+        out[name] = O.mcmc_threaded(pima["chain_init"], k, 1, len(ref))
+    np.testing.assert_array_equal(out["F"], ref)                       # same layout: identical
+    d = np.max(np.abs(out["C"] - ref), axis=1)
+    assert d[:25].max() < 1e-9                                         # the prefix the GPU test compares
+    assert d.max() > 1e-3                                              # ... and then it is a different chain
+    first = int(np.argmax(d > 1e-6))
+    assert 25 < first < len(ref)
+    # both layouts evaluate the same function: one step from any reference state agrees to rounding
+    tf = O.Target(np.asfortranarray(pima["X"]), pima["y"], pima["pscale"])
+    tc = O.Target(np.ascontiguousarray(pima["X"]), pima["y"], pima["pscale"])
+    for i in (0, first, len(ref) - 1):
+        assert tc.lpost(ref[i]) == pytest.approx(tf.lpost(ref[i]), rel=1e-13)
+        np.testing.assert_allclose(tc.glp(ref[i]), tf.glp(ref[i]), rtol=1e-9, atol=1e-9)
