@@ -222,6 +222,11 @@ __global__ void __launch_bounds__(kBlock, 2) eval_persist_kernel(const EvalArgs 
       const long long row0 = cur * RB;
       if (!loaded) load_batch(cur);
       loaded = false;
+      // the index of the batch after this one, while the loads are in flight: static stride as
+      // long as the prefix lasts, then a draw from the pool
+      ++ks;
+      if (tid == 0) producer_visit();
+      const long long nxt = ks < KS ? bt0 + ks * nwarps : next_dynamic();
       bool y1[M], valid[M];
 #pragma unroll
       for (int j = 0; j < M; ++j) {
@@ -279,10 +284,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_persist_kernel(const EvalArgs 
 #pragma unroll
           for (int i = 0; i < V; ++i) acc[sl][i] += (double)gb[sl][i];
       }
-      // next batch: static stride while the prefix lasts, then the claim that is already back
-      ++ks;
-      if (tid == 0) producer_visit();
-      cur = ks < KS ? bt0 + ks * nwarps : next_dynamic();
+      cur = nxt;
     }
     EV_STAMP(2);
 

@@ -139,6 +139,7 @@ struct lrb_handle {
   unsigned int* work = nullptr;
   int* drive_abort = nullptr;
   double* drive_acc = nullptr;
+  bool capturing = false;     // inside build_graph's stream capture: static kernels only
   bool drive = true;          // LRB_DRIVE=0 / LRB_DETERMINISTIC=1: static fixed-order kernel, one launch per evaluation
   int grid_drive = 0, grid_drive_nograd = 0;
   long long drive_spin_ns = 20ll * 1000 * 1000 * 1000;
@@ -415,7 +416,7 @@ FinishArgs finish_args(lrb_handle* h, const double* beta, SamplerState* st) {
 }
 
 bool drive_ok(const lrb_handle* h, bool want_grad) {
-  return h->drive && (want_grad ? h->grid_drive : h->grid_drive_nograd) > 0;
+  return h->drive && !h->capturing && (want_grad ? h->grid_drive : h->grid_drive_nograd) > 0;
 }
 
 // Drive mode: ONE cooperative launch performs `n_evals` consecutive evaluations (dynamic batch
@@ -1099,7 +1100,9 @@ int build_graph(lrb_handle* h, int nodes, bool want_grad) {
   const long long kl = h->kernel_launches, el = h->eval_launches;
   CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int rc = LRB_OK;
+  h->capturing = true;     // graphs hold the static kernel (one launch per evaluation)
   for (int i = 0; i < nodes && rc == LRB_OK; ++i) rc = enqueue_run_eval(h);
+  h->capturing = false;
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
   h->graph_kl_per_replay = h->kernel_launches - kl;

@@ -43,8 +43,9 @@ def test_chain_resumes_in_a_new_handle_at_counter_t0(lr, pima, kind):
     assert c.chain_state()[2] == 100
     # without t0 the stream restarts at counter 0: a different chain
     d = lr.Problem(deterministic=True).bind_data(X, pima["y"], pima["pscale"])
-    other, _ = d.run(kernels(lr, d, pima)[kind], x, 2, 30, seed=2024, init_lpost=lp)
-    assert np.max(np.abs(other - rest)) > 0
+    other, acc_o = d.run(kernels(lr, d, pima)[kind], x, 2, 30, seed=2024, init_lpost=lp)
+    if acc2 > 0 or acc_o > 0:     # (the Pima MALA tuning can sit still for 60 steps)
+        assert np.max(np.abs(other - rest)) > 0
 
 
 @pytest.mark.parametrize("kind", ["rwmh", "hmc"])
