@@ -32,7 +32,7 @@ prob = bind_data(X, y, pscale)                                # the one extra li
 
 init = np.random.randn(p) * 0.1                               # fit-numpy.py:26
 print("MAP:")
-res = map_estimate(prob, init)                                # fit-np-ul.py:54
+res = map_estimate(prob, init, method="BFGS")                 # fit-np-ul.py:54 (method="newton": fit-jax.py:62-79 on the device)
 print(res.x, ll(res.x), glp(res.x))
 
 pre = np.array([100., 1., 1., 1., 1., 1., 25., 1.])            # fit-np-mala.py:97

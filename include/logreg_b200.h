@@ -206,6 +206,31 @@ int lrb_tc_tile_rows(void);
 int lrb_debug_timeline(lrb_handle* h, int enable);
 int lrb_debug_timeline_read(lrb_handle* h, int64_t* out, int64_t cap, int64_t* grid);
 
+/* ---- MAP optimiser: the step before the samplers (provides `init`) ---------------------
+ * Newton's method with the exact Hessian and step halving, Python/fit-jax.py:62-79 (same loop
+ * in fit-jax2.py and fit-jax-ul.py): step = solve(X'WX + diag(pscale^-2), glp(beta)), halved up
+ * to 15 times until lpost improves, stop when ||glp|| < tol at the iterate the step came from
+ * (the reference uses tol = 0.01, maxit = 500).  lpost/glp come from the fused kernel (one pass
+ * each), X'WX from a float64 block kernel, the Cholesky solve and the accept/halve decision run
+ * on the device; the host sequences launches and reads one flag per trial.  init, beta_out: p
+ * doubles (host).  Row-sharded handles need the NCCL communicator (p x p allreduce). */
+typedef struct lrb_map_info {
+  int32_t iterations;  /* Newton iterations performed */
+  int32_t converged;   /* 1 if ||glp|| < tol was reached within maxit */
+  int32_t halvings;    /* step halvings over the whole run */
+  int32_t evals;       /* fused evaluations (passes over X for lpost / glp) */
+  double lpost;        /* lpost at beta_out */
+  double grad_norm;    /* ||glp||_2 at the last iterate a step was computed from */
+} lrb_map_info;
+int lrb_map(lrb_handle* h, const double* init, double tol, int maxit, double* beta_out, lrb_map_info* info);
+/* H_out (p x p, row-major, host) = X'WX + diag(pscale^-2) = -Hessian of lpost at beta
+ * (jacfwd(jacrev(lpost)) in fit-jax.py:58-61, up to the sign). */
+int lrb_hessian(lrb_handle* h, const double* beta, double* H_out);
+/* The Cholesky solve lrb_map runs on the device, callable on the host (it is the same
+ * __host__ __device__ code): A (p x p, lower triangle used, overwritten) += diag(pscale^-2),
+ * step = A^-1 g.  Returns 0 or k+1 if A is not positive definite at column k.  No GPU needed. */
+int lrb_debug_chol_solve(double* A, int ld, int p, const double* pscale, const double* g, double* step);
+
 /* lprior alone (fit-np-ul.py:33-34; no pass over X). beta: C x p host; out: C. */
 int lrb_lprior(lrb_handle* h, const double* beta, int C, double* out);
 

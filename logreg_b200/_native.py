@@ -35,6 +35,11 @@ class SamplerParams(C.Structure):
                 ("rng", C.c_int32), ("flags", C.c_int32), ("init_lpost", C.c_double), ("t0", C.c_int64)]
 
 
+class MapInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("halvings", C.c_int32), ("evals", C.c_int32),
+                ("lpost", C.c_double), ("grad_norm", C.c_double)]
+
+
 class Info(C.Structure):
     _fields_ = [("n", C.c_int64), ("p", C.c_int32), ("p_pad", C.c_int32), ("mode", C.c_int32),
                 ("grid", C.c_int32), ("block", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
@@ -62,6 +67,9 @@ SIGNATURES = {
     "lrb_eval": (_i, [_vp, _dp, _i, _i, _dp, _dp, _dp]),
     "lrb_eval_device": (_i, [_vp, _vp, _vp, _i]),
     "lrb_lprior": (_i, [_vp, _dp, _i, _dp]),
+    "lrb_map": (_i, [_vp, _dp, C.c_double, _i, _dp, C.POINTER(MapInfo)]),
+    "lrb_hessian": (_i, [_vp, _dp, _dp]),
+    "lrb_debug_chol_solve": (_i, [_dp, _i, _i, _dp, _dp, _dp]),
     "lrb_debug_tc_eta": (_i, [_vp, _dp, _i, C.POINTER(C.c_float)]),
     "lrb_tc_tile_rows": (_i, []),
     "lrb_debug_timeline": (_i, [_vp, _i]),

@@ -233,6 +233,25 @@ class Problem:
     def glp(self, beta):
         return self.eval(beta, want_grad=True)[2].copy()
 
+    # ------------------------------------------------------------ MAP (the step before the samplers)
+    def map(self, init, tol=0.01, maxit=500):
+        """Newton's method with the exact Hessian and step halving on the device (lrb_map;
+        Python/fit-jax.py:62-79, whose tol = 0.01 and maxit = 500 are the defaults).
+        Returns (beta, info dict)."""
+        b0 = self._beta(init)
+        out = np.empty(self.p)
+        inf = N.MapInfo()
+        self._ck(self._lib.lrb_map(self._h, N.as_dp(b0), float(tol), int(maxit), N.as_dp(out), C.byref(inf)))
+        self._cache_key = None
+        return out, {k: getattr(inf, k) for k, _ in N.MapInfo._fields_}
+
+    def hessian(self, beta):
+        """X'WX + diag(pscale^-2) = -Hessian of lpost at beta, (p, p) float64 (lrb_hessian)."""
+        b = self._beta(beta)
+        H = np.empty((self.p, self.p))
+        self._ck(self._lib.lrb_hessian(self._h, N.as_dp(b), N.as_dp(H)))
+        return H
+
     # ------------------------------------------------------------ sampler runs
     def _params(self, k, seed, rng, init_lpost, flags=0, t0=0):
         sp = N.SamplerParams()

@@ -182,10 +182,11 @@ __global__ void __launch_bounds__(kBlock, 2) eval_persist_kernel(const EvalArgs 
       const unsigned int chunk = c / kPoolChunk, slot = c % kPoolChunk;
       unsigned int base = 0xffffffffu;   // exhausted unless a published chunk says otherwise
       if (lane == 0) {
-        for (;;) {
+        for (unsigned int spins = 0;; ++spins) {
           if (s_tag[chunk % kPoolSlots] == chunk + 1u) { __threadfence_block(); base = s_base[chunk % kPoolSlots]; break; }
           if (chunk >= s_last) break;
           if (warp == 0) producer_visit();   // the producer must not wait for itself
+          if (spins > (1u << 28)) { *pa.abort = 1; break; }   // never seen; a bug here must not hang the GPU
         }
       }
       base = __shfl_sync(0xffffffffu, base, 0);

@@ -62,22 +62,30 @@ def init_comm(problem, kind: str = "p2p"):
     if world == 1:
         return problem
     if kind == "auto":
+        # Every collective stays OUTSIDE the try blocks: a rank whose export or connect fails must
+        # still take part in the all_gather / all_reduce, or the others would wait for it forever.
         ok = 1
+        mine = C.create_string_buffer(64)
         try:
-            mine = C.create_string_buffer(64)
             N.check(lib.lrb_comm_p2p_export(problem._h, mine), problem._h)
-            allh = _allgather_bytes(mine.raw)
-            N.check(lib.lrb_comm_p2p_connect(problem._h, rank, world, C.create_string_buffer(allh, 64 * world)), problem._h)
         except Exception:
-            ok = 0
+            ok = 0                                   # gathers a dummy (zero) handle
+        allh = _allgather_bytes(mine.raw)
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
         t = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)     # can everybody export?
         if int(t.item()) == 1:
-            dist.barrier()
+            try:
+                N.check(lib.lrb_comm_p2p_connect(problem._h, rank, world, C.create_string_buffer(allh, 64 * world)), problem._h)
+            except Exception:
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # could everybody map its peers?
+        if int(t.item()) == 1:
+            dist.barrier()                           # nobody writes a mailbox before every rank has cleared its own
             problem.world, problem.rank, problem.comm_kind = world, rank, "p2p"
             return problem
-        kind = "nccl"     # some rank could not map peer memory: everyone falls back together
+        kind = "nccl"     # some rank could not export / map peer memory: everyone falls back together
     if kind == "nccl":
         libnccl = _build.nccl_library().encode()
         uid = C.create_string_buffer(128)

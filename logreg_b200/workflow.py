@@ -4,7 +4,12 @@ device kernels: data ingest (f2), MAP initialisation (f1), output + summaries (f
 Reference lines mirrored (paths relative to the reference root):
     load_pima       Python/fit-numpy.py:12-19 (parquet -> X with a ones column, y float32)
                     C/fit-bayes.c:46-68 reads the same table from the text file pima.data
-    map_estimate    Python/fit-np-ul.py:54  minimize(-lpost, init, jac=-glp, method='BFGS')
+    map_estimate    method="newton": Python/fit-jax.py:62-79, Newton with the exact Hessian and step
+                    halving, on the device (lrb_map: X'WX block kernel, Cholesky solve, decisions);
+                    method="BFGS": Python/fit-np-ul.py:54  minimize(-lpost, init, jac=-glp, method='BFGS'),
+                    SciPy on the host around the fused evaluation (one pass per iteration)
+    describe_device running mean / covariance accumulated on the device during the run (lrb_run_moments;
+                    Dex/djwutils.dx:97-103 meanAndCovariance)
     save_samples    Python/fit-numpy.py:89-90  DataFrame(out, columns=b0..).to_parquet(...)
     describe        Python/fit-numpy.py:92-96  scipy.stats.describe(out): mean / variance
 """
@@ -33,11 +38,31 @@ def load_pima(path):
     return np.asfortranarray(np.hstack((np.ones((len(rows), 1)), X))), y
 
 
-def map_estimate(problem, init, method="BFGS", **kw):
-    """MAP by quasi-Newton with the hand-coded gradient, as fit-np-ul.py:54. lpost and glp at the
-    same point come from ONE fused pass over X (the reference spends three per iteration)."""
-    from scipy.optimize import minimize
+class MapResult(dict):
+    """Result of map_estimate: attribute access like scipy's OptimizeResult (x, fun, nit, success)."""
+    __getattr__ = dict.__getitem__
+
+
+def map_estimate(problem, init, method="newton", tol=None, maxit=None, **kw):
+    """MAP estimate, the `init` of the samplers.
+
+    method="newton" (default): the reference's Newton loop (fit-jax.py:62-79) entirely on the
+        device -- gradient and lpost from the fused kernel, the Hessian X'WX + diag(pscale^-2) from
+        a float64 block kernel, Cholesky solve and step halving in device kernels (lrb_map).
+        tol (default 0.01, the reference's) bounds ||glp||; maxit defaults to 500.
+    method="BFGS" (or any scipy.optimize.minimize method): quasi-Newton with the hand-coded gradient
+        as fit-np-ul.py:54; lpost and glp at the same point come from ONE fused pass over X (the
+        reference spends three per iteration), the iteration itself runs in SciPy on the host."""
     init = np.asarray(init, dtype=np.float64)
+    if method.lower() == "newton":
+        x, info = problem.map(init, tol=0.01 if tol is None else tol, maxit=500 if maxit is None else maxit)
+        return MapResult(x=x, fun=-info["lpost"], nit=info["iterations"], success=bool(info["converged"]),
+                         nfev=info["evals"], halvings=info["halvings"], grad_norm=info["grad_norm"], method="newton")
+    from scipy.optimize import minimize
+    if tol is not None:
+        kw.setdefault("tol", tol)
+    if maxit is not None:
+        kw.setdefault("options", {}).setdefault("maxiter", maxit)
 
     def fun(b):
         lp, _, g = problem.eval(b, want_grad=True)
@@ -45,6 +70,14 @@ def map_estimate(problem, init, method="BFGS", **kw):
 
     res = minimize(fun, init, jac=True, method=method, **kw)
     return res
+
+
+def describe_device(problem, pooled=True):
+    """The same summary from the moments the device accumulated during run(..., moments=True):
+    nothing but O(p^2) numbers crosses the bus (what config 4's 4096 chains need)."""
+    n, mean, cov = problem.moments(pooled=pooled, cov=True)
+    var = np.diagonal(cov, axis1=-2, axis2=-1)
+    return {"nobs": n, "mean": mean, "variance": var, "covariance": cov}
 
 
 def describe(mat):

@@ -109,3 +109,26 @@ def test_header_is_plain_c_and_links(tmp_path):
         assert run.returncode == 0 and "lpost" in run.stdout, run.stderr
     else:
         assert run.returncode == 1 and "no CUDA device" in run.stderr
+
+
+def test_newton_cholesky_solve_on_the_host():
+    """lrb_map's Cholesky solve is __host__ __device__ code: check it here against NumPy
+    (A + diag(pscale^-2)) step = g, and its not-positive-definite report."""
+    from logreg_b200 import _native as N
+    lib = N.load()
+    rs = np.random.RandomState(0)
+    for p in (1, 2, 8, 64, 130):
+        M = rs.randn(p + 5, p)
+        A = M.T @ M
+        ps = 0.5 + rs.rand(p)
+        g = rs.randn(p)
+        ld = p + 3
+        buf = np.zeros((p, ld))
+        buf[:, :p] = A
+        step = np.zeros(p)
+        rc = lib.lrb_debug_chol_solve(N.as_dp(buf), ld, p, N.as_dp(ps), N.as_dp(g), N.as_dp(step))
+        assert rc == 0
+        np.testing.assert_allclose(step, np.linalg.solve(A + np.diag(1 / ps ** 2), g), rtol=1e-9, atol=1e-12)
+    bad = np.array([[1.0, 2.0], [2.0, 1.0]]) - np.eye(2)      # minus the prior term: indefinite
+    step = np.zeros(2)
+    assert lib.lrb_debug_chol_solve(N.as_dp(bad), 2, 2, N.as_dp(np.ones(2)), N.as_dp(np.ones(2)), N.as_dp(step)) == 2

@@ -73,3 +73,77 @@ def test_row_sharded_sum_equals_full_evaluation():
     for (l0, g0), (l1, g1) in zip(results[0][1], results[1][1]):
         assert l0 == l1
         np.testing.assert_array_equal(g0, g1)
+
+
+class _FakeLib:
+    """Stands in for liblogreg_b200 in the communicator bootstrap: records the calls and fails
+    where told, so the collective sequence of dist.init_comm can be checked on CPU."""
+
+    def __init__(self, fail_export=False, fail_connect=False):
+        self.fail_export, self.fail_connect, self.calls = fail_export, fail_connect, []
+
+    def lrb_comm_p2p_export(self, h, buf):
+        self.calls.append("export")
+        return 3 if self.fail_export else 0
+
+    def lrb_comm_p2p_connect(self, h, rank, world, handles):
+        self.calls.append("connect")
+        return 3 if self.fail_connect else 0
+
+    def lrb_nccl_unique_id(self, uid, path):
+        self.calls.append("uid")
+        return 0
+
+    def lrb_comm_init_nccl(self, h, rank, world, uid, path):
+        self.calls.append("nccl")
+        return 0
+
+
+class _FakeProblem:
+    def __init__(self, lib):
+        self._lib, self._h = lib, None
+
+
+def _comm_worker(rank, world, port, q, scenario):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        from logreg_b200 import dist as lrd
+        lib = _FakeLib(fail_export=(scenario == "export" and rank == 1), fail_connect=(scenario == "connect" and rank == 0))
+        prob = _FakeProblem(lib)
+        lrd.init_comm(prob, "auto")
+        q.put((rank, prob.comm_kind, lib.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("scenario,kind", [("ok", "p2p"), ("export", "nccl"), ("connect", "nccl")])
+def test_comm_auto_falls_back_jointly_without_a_collective_mismatch(scenario, kind):
+    """if ONE rank cannot export / map peer memory, every rank must still run the same
+    collectives and all fall back to NCCL together (no rank left waiting in an all_gather)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q, scenario)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, got, calls in results:
+        assert got == kind, (scenario, rank, got, calls)
+        assert calls[0] == "export"
+        if kind == "p2p":
+            assert calls == ["export", "connect"]
+        else:
+            assert calls[-1] == "nccl"
+            if scenario == "export":
+                assert "connect" not in calls          # nobody maps peers when an export failed

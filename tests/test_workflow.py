@@ -54,7 +54,7 @@ def test_map_estimate_matches_reference_map(pima):
     prob = lr.bind_data(np.asfortranarray(pima["X"]), pima["y"], pima["pscale"])
     b0 = np.array([-9.8, 0.1, 0.03, -0.005, 0.0, 0.08, 1.8, 0.04])
     before = prob.info()["eval_launches"]
-    res = map_estimate(prob, b0)
+    res = map_estimate(prob, b0, method="BFGS")
     used = prob.info()["eval_launches"] - before
     np.testing.assert_allclose(res.x, pima["map"], rtol=1e-5, atol=1e-6)
     assert -res.fun == pytest.approx(-100.44943693563214, rel=1e-10)
