@@ -294,5 +294,64 @@ def test_fp32_mode_against_fp64_mode_at_scale():
     d64 = b.eval(q1)[0] - b.eval(q0)[0]
     print(f"fp32-vs-fp64 at n=2e7: max |dlpost| = {worst_abs:.3e}, max |dglp| = {worst_g:.3e}, "
           f"lpost difference error = {abs(d32 - d64):.3e} (difference {d64:.3f})")
-    assert worst_abs < 0.5
-    assert abs(d32 - d64) < 0.05
+    # measured on B200 (round 1 and 2): 0.078 and 6.5e-4; the bounds are 3x that
+    assert worst_abs < 0.25
+    assert abs(d32 - d64) < 2e-3
+
+
+def test_fp32_mode_at_the_headline_shape_decides_like_fp64_mode():
+    """Config 3's shape (n = 1e8, p = 64): |lpost| is about 6e7 while an accept/reject decision
+    hangs on differences of O(1).  On identical rows, (1) the FP32-storage mode must give lpost
+    DIFFERENCES between points one posterior sd apart to < 5e-3 of the FP64-mode ones, and (2) its
+    device HMC chain (L = 20, the bench tuning) must take the decisions of the reference HMC kernel
+    run in FP64 mode with the same draws over 50 iterations -- identical except where
+    |log alpha - log u| falls inside that 5e-3 (BASELINE.json north_star), where the comparison
+    stops.  77 GB of HBM: skipped on a device that cannot hold both copies."""
+    import logreg_b200 as lr
+    n, p, L, iters, seed = 100_000_000, 64, 20, 50, 2026
+    try:
+        a, b = lr.Problem(), lr.Problem()
+        bt = a.gen_synthetic(n, p, mode="fp32", seed=42)
+        b.gen_synthetic(n, p, mode="fp64", seed=42, beta_true=bt)
+    except lr.LogregB200Error as e:
+        if "memory" in str(e).lower():
+            pytest.skip("needs ~77 GB of device memory")
+        raise
+    Xa, ya = a.copy_rows(n - 500, 500)
+    Xb, yb = b.copy_rows(n - 500, 500)
+    np.testing.assert_array_equal(Xa, Xb)
+    np.testing.assert_array_equal(ya, yb)
+    rs = np.random.RandomState(5)
+    sd = 2.2 / np.sqrt(n)
+    worst = 0.0
+    for _ in range(3):
+        q0, q1 = bt + sd * rs.randn(p), bt + sd * rs.randn(p)
+        d32 = a.lpost(q1) - a.lpost(q0)
+        d64 = b.lpost(q1) - b.lpost(q0)
+        worst = max(worst, abs(d32 - d64))
+    # (2) the device chain in FP32 mode ...
+    eps = 5.0 * sd / L
+    k32 = lr.hmcKernel(a.lpost, a.glp, eps=eps, l=L, dmm=1.0)
+    mat32, acc32 = a.run(k32, bt, 1, iters, seed=seed)
+    # ... against the reference kernel (oracle port, fit-np-hmc.py:56-87) over the FP64-mode density
+    Z, U = a.rng_dump(seed, 0, iters)
+    trace = []
+    ref_kernel = O.hmc_kernel(b.lpost, b.glp, eps=eps, l=L, dmm=1.0, rng=O.ReplayRNG(Z, U), trace=trace)
+    x, compared, min_margin, tie_at = bt, 0, np.inf, None
+    for i in range(iters):
+        x_new = ref_kernel(x)
+        log_alpha, log_u, acc_ref = trace[-1]
+        acc_dev = bool(np.any(mat32[i] != (mat32[i - 1] if i else bt)))
+        if acc_dev != bool(acc_ref):
+            assert abs(log_alpha - log_u) <= 5e-3, (i, log_alpha, log_u)   # only a tie of the accept test may differ
+            tie_at = i
+            break
+        min_margin = min(min_margin, abs(log_alpha - log_u))
+        assert np.max(np.abs(mat32[i] - x_new)) <= 1e-2 * sd, (i, np.max(np.abs(mat32[i] - x_new)) / sd)
+        x = x_new
+        compared += 1
+    n_acc = int(sum(t[2] for t in trace[:compared]))
+    print(f"fp32 mode at n=1e8: lpost difference error {worst:.3e}; {compared} HMC decisions compared "
+          f"({n_acc} accepts), closest |log alpha - log u| {min_margin:.3e}, tie at {tie_at}")
+    assert worst < 5e-3
+    assert compared >= 25 and 0 < n_acc < compared
