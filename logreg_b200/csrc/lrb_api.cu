@@ -141,6 +141,8 @@ struct lrb_handle {
   int* drive_abort = nullptr;
   double* drive_acc = nullptr;
   bool capturing = false;     // inside build_graph's stream capture: static kernels only
+  bool chain_live_partial = false;    // launch_run: at least one drive chunk of the current run is enqueued
+  bool drive_launch_failed = false;   // a cooperative launch was refused: static kernel from then on
   bool drive_multi = false;   // experimental: drive mode on row-sharded handles (LRB_DRIVE_MULTI=1)
   bool drive = true;          // LRB_DRIVE=0 / LRB_DETERMINISTIC=1: static fixed-order kernel, one launch per evaluation
   int grid_drive = 0, grid_drive_nograd = 0;
@@ -447,7 +449,15 @@ int enqueue_drive(lrb_handle* h, const double* beta, SamplerState* st, bool want
   void* fn = (void*)(want_grad ? h->kern.drive : h->kern.drive_nograd);
   const int grid = want_grad ? h->grid_drive : h->grid_drive_nograd;
   void* args[2] = {&a, &pa};
-  CK(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, 0, h->stream));
+  cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, 0, h->stream);
+  if (le != cudaSuccess) {
+    // e.g. the device is shared and the grid cannot be co-resident: nothing was enqueued; the
+    // callers fall back to the static kernel (one launch per evaluation) for the rest of this handle
+    cudaGetLastError();
+    h->drive = false;
+    h->drive_launch_failed = true;
+    return fail(h, LRB_E_CUDA, "cooperative launch of the drive-mode kernel failed: %s", cudaGetErrorString(le));
+  }
   h->kernel_launches++;
   h->eval_launches += n_evals;
   if (nccl_mode) {
@@ -475,7 +485,11 @@ int check_drive(lrb_handle* h) {
 
 // Enqueue one fused evaluation at `beta` (device) on h->stream.
 int enqueue_eval(lrb_handle* h, const double* beta, SamplerState* st, bool want_grad) {
-  if (drive_ok(h, want_grad)) return enqueue_drive(h, beta, st, want_grad, 1);
+  if (drive_ok(h, want_grad)) {
+    const int rc = enqueue_drive(h, beta, st, want_grad, 1);
+    if (rc == LRB_OK || !h->drive_launch_failed) return rc;
+    // the cooperative launch was refused before anything ran: use the static kernel instead
+  }
   EvalArgs a{};
   a.X = h->X;
   a.y = h->y;
@@ -1382,14 +1396,20 @@ int launch_run(lrb_handle* h) {
   const bool nccl_mode = (h->comm == 1 && h->world > 1);
   if (h->run_C == 1 && !nccl_mode && drive_ok(h, h->run_want_grad)) {
     // drive mode: the whole run is one launch (chunked only to keep the counter in an int)
+    bool refused = false;
     while (needed > 0) {
       const int chunk = (int)std::min<long long>(needed, 1ll << 24);
       int rc = enqueue_drive(h, h->state->beta_in, h->state, h->run_want_grad, chunk);
+      if (rc && h->drive_launch_failed && !h->chain_live_partial) { refused = true; break; }   // nothing ran yet: static path below
       if (rc) return rc;
+      h->chain_live_partial = true;
       needed -= chunk;
     }
-    h->chain_live = true;
-    return LRB_OK;
+    h->chain_live_partial = false;
+    if (!refused) {
+      h->chain_live = true;
+      return LRB_OK;
+    }
   }
   // graph of up to 64 evaluations, replayed; the remainder goes out as plain launches
   const int nodes = (int)std::min<long long>(64, needed);
