@@ -484,17 +484,18 @@ def main():
     bytes_eval_rank = inf1["bytes_per_eval"]            # this rank's shard
     kern_ms = ms_total / evals                           # per evaluation: includes the in-kernel allreduce + sampler update
     achieved = bytes_eval_rank / (kern_ms * 1e-3) / 1e9
+    is_drive = launches < evals     # drive mode: one launch for the whole timed region (single-GPU handles)
     traffic, traffic_src = None, None
     try:
         if world == 1 and not args.n:   # the committed ncu capture is of the single-GPU kernel
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = args.workload + ("_static" if args.deterministic else "")
+            key = args.workload + ("" if is_drive else "_static")
             traffic = tj.get(key, {}).get("bytes_per_eval") * evals / max(1, launches)
             traffic_src = tj.get(key, {}).get("source")
     except Exception:
         pass
     tname = "float" if w["mode"] == "fp32" else "double"
-    kname = ("lrb::eval_kernel<%s,%d,grad>" if args.deterministic else "lrb::eval_persist_kernel<%s,%d,grad>") % (tname, inf1["p_pad"])
+    kname = ("lrb::eval_persist_kernel<%s,%d,grad>" if is_drive else "lrb::eval_kernel<%s,%d,grad>") % (tname, inf1["p_pad"])
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
@@ -504,7 +505,8 @@ def main():
             "avg_launch_ms": ms_total / max(1, launches), "avg_eval_ms": kern_ms,
             "note": "drive mode: ONE cooperative launch performs all K*L evaluations of the timed region; "
                     "achieved = algorithmic bytes of the launch / its duration (CUDA events on the launching stream)"
-                    if not args.deterministic else "static kernel: one launch per evaluation"}
+                    if is_drive else "static kernel: one launch per evaluation (replayed CUDA graph); row-sharded handles "
+                                     "always run this kernel, the fused peer-memory exchange is inside it"}
 
     # ---- secondary workloads (configs 2 and 4), after the headline measurement
     secondary = None
@@ -567,7 +569,7 @@ def main():
                             "single_call_value = one mcmc(iters=K) call"},
             "digest": digest, "secondary": secondary,
             "gpu_launches": int(launches), "gpu_evals": int(evals),
-            "mode": "static" if args.deterministic else "drive",
+            "mode": "drive" if is_drive else "static",
             "comm": (getattr(prob, "comm_kind", args.comm) if world > 1 else None), "clocks": clk}
     print(json.dumps(line))
     return finish()

@@ -137,11 +137,13 @@ int lrb_set_stream(lrb_handle* h, void* cuda_stream);
 int lrb_synchronize(lrb_handle* h);
 
 /* Per-handle options.
- *   DETERMINISTIC  0 (default): single-chain evaluations run in "drive mode" -- a persistent
- *                  cooperative kernel with dynamic row-batch scheduling and atomic (timing-ordered)
- *                  accumulation of the CTA sums; results are reproducible to rounding (~1e-15
- *                  relative), not bit for bit.  1: the static kernel, one launch per evaluation,
- *                  CTA sums added in a fixed order => bit-identical results for a fixed shape.
+ *   DETERMINISTIC  0 (default): single-chain evaluations on a single-GPU handle run in "drive
+ *                  mode" -- a persistent cooperative kernel (one launch per run) with dynamic
+ *                  row-batch scheduling and atomic (timing-ordered) accumulation of the CTA sums;
+ *                  results are reproducible to rounding (~1e-15 relative), not bit for bit.
+ *                  1: the static kernel, one launch per evaluation (replayed CUDA graph), CTA sums
+ *                  added in a fixed order => bit-identical results for a fixed shape.  Row-sharded
+ *                  handles (world > 1) and many-chain runs always use the static kernels.
  *   TC_MIN_CHAINS  chain count from which the tensor-core many-chain kernel is used (default 12).
  *   P2P_TIMEOUT_MS bound of every in-kernel wait for a peer rank / another CTA (default 60000).
  *   PDL            programmatic dependent launch between evaluations of the static kernel.

@@ -111,3 +111,31 @@ def test_philox_known_answer():
     assert philox_ref([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox_ref([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_front_end_namespaces_export_the_reference_names():
+    """The three import switches (fit-np-*.py, fit-np-hmc.py, fit-jax*.py) expose the names those
+    scripts define; importing them needs no GPU."""
+    import logreg_b200 as top
+    import logreg_b200.jaxlike as J
+    import logreg_b200.np_hmc as H
+    for name in ("ll", "lprior", "lpost", "glp", "mhKernel", "ulKernel", "malaKernel", "hmcKernel", "mcmc", "bind_data"):
+        assert callable(getattr(top, name))
+    for name in ("ll", "lprior", "lpost", "glp", "mhKernel", "hmcKernel", "mcmc", "bind_data"):
+        assert callable(getattr(H, name))
+    for name in ("ll", "lprior", "lpost", "glp", "mhKernel", "ulKernel", "malaKernel", "hmcKernel", "mcmc", "bind_data",
+                 "PRNGKey", "split", "normal", "uniform"):
+        assert callable(getattr(J, name))
+    import inspect
+    assert list(inspect.signature(J.mcmc).parameters)[:4] == ["init", "kernel", "thin", "iters"]      # fit-jax2.py:98
+    assert list(inspect.signature(H.mhKernel).parameters) == ["lpost", "rprop"]                         # fit-np-hmc.py:56
+    assert list(inspect.signature(top.mhKernel).parameters)[:3] == ["lpost", "rprop", "dprop"]          # fit-numpy.py:53
+    # fit-np-hmc.py's one-argument kernel on plain Python callables (no device involved)
+    np.random.seed(0)
+    k = H.mhKernel(lambda x: -0.5 * float(np.sum(x * x)), lambda x: x + 0.5 * np.random.randn(len(x)))
+    x = np.zeros(3)
+    for _ in range(20):
+        x = k(x)
+    assert x.shape == (3,) and np.all(np.isfinite(x))
+    # keys are plain integers; split is deterministic host arithmetic
+    assert J.PRNGKey(42) == 42 and J.random.split(5, 3) == J.split(5, 3)
