@@ -1506,6 +1506,9 @@ extern "C" int lrb_run(lrb_handle* h, const lrb_sampler_params* params, const do
   }
   // row-sharded with the fused peer-memory allreduce: chains one after the other
   if (!init) return fail(h, LRB_E_BAD_ARG, "continuing (init == NULL) needs C == 1 in this configuration");
+  if (params && (params->flags & LRB_RUN_MOMENTS))
+    return fail(h, LRB_E_UNSUPPORTED, "LRB_RUN_MOMENTS with several chains on a fused-P2P row-sharded handle is not supported "
+                                      "(the chains run one after the other through one state); use the NCCL communicator");
   const int p = h->p;
   const size_t steps = (size_t)(thin * iters);
   for (int c = 0; c < C; ++c) {
