@@ -43,7 +43,8 @@ struct PersistArgs {
 };
 
 constexpr int kPoolChunk = 8;    // batches per global claim (one per warp of a CTA)
-constexpr int kPoolSlots = 8;    // chunk descriptors in flight per CTA
+constexpr int kPoolSlots = 16;   // chunk descriptors per CTA: the producer runs at most 4 chunks ahead of the draws, so a
+                                 // slot is recycled only 12 chunks (96 draws of this CTA) after its last draw was handed out
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
   unsigned long long v;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kBlock, 2) eval_persist_kernel(const EvalArgs 
   __shared__ double scratch[kWarps];
   __shared__ unsigned int s_ticket;
   // per-CTA batch pool: draw c (shared counter) is slot c%8 of chunk c/8; chunk k's first batch
-  // (relative to dyn0) is published in s_base[k%8] with tag k+1
+  // (relative to dyn0) is published in s_base[k%16] with tag k+1
   __shared__ unsigned int s_claims;
   __shared__ volatile unsigned int s_base[kPoolSlots], s_tag[kPoolSlots];
   __shared__ volatile unsigned int s_last;   // first exhausted chunk of this CTA's pool (0xffffffff: none yet)
@@ -286,6 +287,15 @@ __global__ void __launch_bounds__(kBlock, 2) eval_persist_kernel(const EvalArgs 
           for (int i = 0; i < V; ++i) acc[sl][i] += (double)gb[sl][i];
       }
       cur = nxt;
+    }
+    // The producer may leave the loop only once the END of the pool is published.  It normally gets
+    // here by drawing from a chunk that is already marked exhausted, but when the dynamic region is
+    // not a multiple of 8 batches one chunk straddles the end of X, and an out-of-range slot of THAT
+    // chunk ends the loop with the next (exhausted) chunk possibly still unpublished -- the other warps
+    // of this CTA would wait for it forever (found with tests/test_pool_model.py).  A few more visits
+    // publish it: every claim made from here on lies beyond the end.
+    if (tid == 0) {
+      for (int i = 0; i < 64 && s_last == 0xffffffffu; ++i) producer_visit();
     }
     EV_STAMP(2);
 
